@@ -1,0 +1,403 @@
+"""Device-side objects of the hot path: thin Python owners of the C-ABI handles.
+
+torch is used for device memory, streams and (elsewhere) torch.distributed only; every
+kernel launched from here lives in libat_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_double, c_int, c_int64, c_void_p
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import AT_F32, AT_F64, AT_I32, AT_I64, EpiCol, EpiSegment, call
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def require_cuda():
+    """Fail loudly when the CUDA path cannot run (no silent CPU fallback)."""
+    torch = _torch()
+    _cabi.load()
+    if not torch.cuda.is_available():
+        raise _cabi.NativeLibraryError("no CUDA device available: anemoi_transform_b200 has no CPU fallback")
+    return torch
+
+
+def stream_ptr() -> c_void_p:
+    torch = _torch()
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t) -> c_void_p:
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(None)
+
+
+def _np_dtype_code(a: np.ndarray, kinds: dict) -> int:
+    try:
+        return kinds[a.dtype.type]
+    except KeyError:
+        raise TypeError(f"unsupported dtype {a.dtype}") from None
+
+
+_FLOAT_CODES = {np.float32: AT_F32, np.float64: AT_F64}
+_INT_CODES = {np.int32: AT_I32, np.int64: AT_I64}
+
+
+def round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+class CsrMatrix:
+    """A CSR interpolation matrix staged once in HBM (reference: MIRMatrix.__init__,
+    filters/fields/regrid.py:281-285)."""
+
+    def __init__(self, data: np.ndarray, indices: np.ndarray, indptr: np.ndarray, shape: Sequence[int]):
+        require_cuda()
+        data = np.ascontiguousarray(data)
+        indices = np.ascontiguousarray(indices)
+        indptr = np.ascontiguousarray(indptr)
+        if data.dtype not in (np.float32, np.float64):
+            data = data.astype(np.float64)
+        if indices.dtype not in (np.int32, np.int64):
+            indices = indices.astype(np.int64)
+        if indptr.dtype not in (np.int32, np.int64):
+            indptr = indptr.astype(np.int64)
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(data.shape[0])
+        self.dtype = data.dtype
+        if indptr.shape[0] != self.shape[0] + 1:
+            raise ValueError(f"indptr has {indptr.shape[0]} entries for {self.shape[0]} rows")
+        if indices.shape[0] != self.nnz:
+            raise ValueError("indices and data differ in length")
+        h = c_void_p()
+        call(
+            "at_csr_create",
+            self.shape[0],
+            self.shape[1],
+            self.nnz,
+            indptr.ctypes.data_as(c_void_p),
+            _np_dtype_code(indptr, _INT_CODES),
+            indices.ctypes.data_as(c_void_p),
+            _np_dtype_code(indices, _INT_CODES),
+            data.ctypes.data_as(c_void_p),
+            _np_dtype_code(data, _FLOAT_CODES),
+            byref(h),
+        )
+        self._h = h
+        u = c_int()
+        call("at_csr_info", self._h, None, None, None, byref(u), None)
+        self.uniform_nnz = u.value
+
+    @classmethod
+    def from_scipy(cls, m) -> "CsrMatrix":
+        m = m.tocsr()
+        return cls(m.data, m.indices, m.indptr, m.shape)
+
+    @property
+    def handle(self) -> c_void_p:
+        if self._h is None:
+            raise RuntimeError("CsrMatrix used after close()")
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            call("at_csr_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def result_dtype(self, x_dtype):
+        torch = _torch()
+        if self.dtype == np.float64 or x_dtype == torch.float64:
+            return torch.float64
+        return torch.float32
+
+    def apply(self, X, n_fields: int | None = None, out=None, variant: int = 0):
+        """Y[n_rows, ld] = A · X[n_cols, ld]  (point-major batches, torch CUDA tensors)."""
+        torch = _torch()
+        if X.dim() != 2 or X.shape[0] != self.shape[1]:
+            raise ValueError(f"X has shape {tuple(X.shape)}, expected [{self.shape[1]}, fields]")
+        if X.stride(1) != 1:
+            raise ValueError("X must be row-major (unit stride along fields)")
+        n_fields = X.shape[1] if n_fields is None else n_fields
+        ydt = self.result_dtype(X.dtype)
+        if out is None:
+            out = torch.empty((self.shape[0], X.shape[1]), dtype=ydt, device=X.device)
+        code = {torch.float32: AT_F32, torch.float64: AT_F64}
+        call(
+            "at_spmm",
+            self.handle,
+            _ptr(X),
+            code[X.dtype],
+            X.stride(0),
+            _ptr(out),
+            code[out.dtype],
+            out.stride(0),
+            n_fields,
+            variant,
+            stream_ptr(),
+        )
+        return out
+
+
+class Epilogue:
+    """A fused pointwise program (segments + per-output-column parameters)."""
+
+    def __init__(self, segments: Iterable[tuple[int, int, int, int]], cols: Iterable[tuple[float, float, float, int]]):
+        require_cuda()
+        segs = list(segments)
+        cols = list(cols)
+        seg_arr = (EpiSegment * len(segs))(*[EpiSegment(*map(int, s)) for s in segs])
+        col_arr = (EpiCol * len(cols))(*[EpiCol(float(lo), float(hi), float(p), int(fl), 0) for lo, hi, p, fl in cols])
+        h = c_void_p()
+        call("at_epilogue_create", seg_arr, len(segs), col_arr, len(cols), byref(h))
+        self._h = h
+        self.n_out_cols = len(cols)
+        self.n_in_cols = max(s[1] + s[2] for s in segs)
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            call("at_epilogue_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, X, out=None, row_mask=None):
+        """Y = epilogue(X) on a resident point-major batch."""
+        torch = _torch()
+        if out is None:
+            out = torch.zeros((X.shape[0], round_up(self.n_out_cols, 4)), dtype=X.dtype, device=X.device)
+        code = {torch.float32: AT_F32, torch.float64: AT_F64}[X.dtype]
+        call("at_pointwise", self.handle, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, _ptr(row_mask), stream_ptr())
+        return out
+
+    def apply_fused(self, csr: CsrMatrix, X, out=None, row_mask=None):
+        """Y = epilogue(A · X)."""
+        torch = _torch()
+        if out is None:
+            out = torch.zeros((csr.shape[0], round_up(self.n_out_cols, 4)), dtype=torch.float32, device=X.device)
+        call("at_spmm_fused", csr.handle, self.handle, _ptr(X), X.stride(0), _ptr(out), out.stride(0), _ptr(row_mask), stream_ptr())
+        return out
+
+
+class KnnIndex:
+    """Bucketed search structure over float64 xyz sources (replaces cKDTree(points))."""
+
+    def __init__(self, xyz, cell_size: float = 0.0):
+        """xyz: tuple of three float64 arrays (numpy on host or torch CUDA tensors)."""
+        torch = require_cuda()
+        x, y, z = xyz
+        if isinstance(x, torch.Tensor):
+            x, y, z = (t.contiguous().to(torch.float64) for t in (x, y, z))
+            self.n = int(x.shape[0])
+            ptrs = (_ptr(x), _ptr(y), _ptr(z))
+            on_device = 1
+            torch.cuda.current_stream().synchronize()
+        else:
+            x, y, z = (np.ascontiguousarray(a, dtype=np.float64) for a in (x, y, z))
+            self.n = int(x.shape[0])
+            ptrs = tuple(a.ctypes.data_as(c_void_p) for a in (x, y, z))
+            on_device = 0
+        h = c_void_p()
+        call("at_knn_create", *ptrs, self.n, on_device, float(cell_size), byref(h))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            call("at_knn_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def query(self, qxyz, k: int = 1, distance_upper_bound: float = float("inf"), want_ties: bool = False):
+        """→ (idx int64[nq,k], dist float64[nq,k], ties uint8[nq] | None), CUDA tensors."""
+        torch = _torch()
+        qx, qy, qz = (to_device_f64(a) for a in qxyz)
+        nq = int(qx.shape[0])
+        idx = torch.empty((nq, k), dtype=torch.int64, device=qx.device)
+        dist = torch.empty((nq, k), dtype=torch.float64, device=qx.device)
+        ties = torch.empty((nq,), dtype=torch.uint8, device=qx.device) if want_ties else None
+        call("at_knn_query", self._h, _ptr(qx), _ptr(qy), _ptr(qz), nq, int(k), float(distance_upper_bound), _ptr(idx), _ptr(dist), _ptr(ties), stream_ptr())
+        return idx, dist, ties
+
+    def ball_mark(self, qxyz, r: float, mark=None):
+        """mark[j] |= any query within r of source j.  → uint8[n] CUDA tensor."""
+        torch = _torch()
+        qx, qy, qz = (to_device_f64(a) for a in qxyz)
+        if mark is None:
+            mark = torch.zeros((self.n,), dtype=torch.uint8, device=qx.device)
+        call("at_ball_mark", self._h, _ptr(qx), _ptr(qy), _ptr(qz), int(qx.shape[0]), float(r), _ptr(mark), stream_ptr())
+        return mark
+
+    def min_nn_distance(self) -> float:
+        out = c_double()
+        call("at_min_nn_distance", self._h, byref(out), stream_ptr())
+        return out.value
+
+
+def to_device_f64(a):
+    torch = _torch()
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=torch.float64).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).cuda()
+
+
+def compact_mask(mark):
+    """Sorted int64 indices of the non-zero bytes of a uint8 CUDA tensor."""
+    torch = _torch()
+    n = int(mark.shape[0])
+    out = torch.empty((max(n, 1),), dtype=torch.int64, device=mark.device)
+    count = c_int64()
+    call("at_compact_mask", _ptr(mark), n, _ptr(out), byref(count), stream_ptr())
+    return out[: count.value]
+
+
+def cropping_mask_device(lats, lons, north, west, south, east):
+    torch = _torch()
+    la, lo = to_device_f64(lats), to_device_f64(lons)
+    mask = torch.empty((la.shape[0],), dtype=torch.uint8, device=la.device)
+    call("at_cropping_mask", _ptr(la), _ptr(lo), int(la.shape[0]), float(north), float(west), float(south), float(east), _ptr(mask), stream_ptr())
+    return mask
+
+
+def transpose(src, out=None):
+    """out[c, r] = src[r, c] for 2-D CUDA tensors of 4- or 8-byte elements."""
+    torch = _torch()
+    rows, cols = src.shape
+    if src.stride(1) != 1:
+        raise ValueError("transpose: source must have unit stride along its last axis")
+    if out is None:
+        out = torch.empty((cols, rows), dtype=src.dtype, device=src.device)
+    call("at_transpose", _ptr(src), rows, cols, src.stride(0), _ptr(out), out.stride(0), src.element_size(), stream_ptr())
+    return out
+
+
+def gather_rows(X, idx, n_fields: int | None = None, out=None):
+    """out[i, :] = X[idx[i], :] (numpy's data[..., idx] on a point-major batch)."""
+    torch = _torch()
+    idx = idx.to(device=X.device, dtype=torch.int64).contiguous()
+    n_out = int(idx.shape[0])
+    n_fields = X.shape[1] if n_fields is None else n_fields
+    if out is None:
+        out = torch.zeros((n_out, X.shape[1]), dtype=X.dtype, device=X.device)
+    err = torch.zeros((1,), dtype=torch.int32, device=X.device)
+    call("at_gather_rows", _ptr(idx), n_out, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_fields, X.element_size(), _ptr(err), stream_ptr())
+    if int(err.item()) != 0:
+        raise IndexError(f"index out of bounds for axis with size {X.shape[0]}")
+    return out
+
+
+def compare_mask(values, op: int, threshold: float):
+    """uint8 mask = OP(values, threshold) for a 1-D (possibly strided) float32 CUDA tensor."""
+    torch = _torch()
+    n = int(values.shape[0])
+    mask = torch.empty((n,), dtype=torch.uint8, device=values.device)
+    call("at_compare_mask", _ptr(values), values.stride(0) if n > 1 else 1, n, int(op), float(threshold), _ptr(mask), stream_ptr())
+    return mask
+
+
+class DeviceBatch:
+    """A batch of fields resident in HBM, point-major: data[n_points, ld], ld % 4 == 0."""
+
+    def __init__(self, data, n_fields: int):
+        self.data = data
+        self.n_fields = int(n_fields)
+
+    @property
+    def n_points(self) -> int:
+        return int(self.data.shape[0])
+
+    @classmethod
+    def from_host_fields(cls, arrays: Sequence[np.ndarray]) -> "DeviceBatch":
+        """Upload F host fields (each [n_points]) and pack them point-major."""
+        torch = require_cuda()
+        n_fields = len(arrays)
+        if n_fields == 0:
+            raise ValueError("empty batch")
+        n_points = int(np.asarray(arrays[0]).size)
+        dtype = np.result_type(*[np.asarray(a).dtype for a in arrays])
+        if dtype not in (np.float32, np.float64):
+            dtype = np.dtype(np.float64)
+        host = np.empty((n_fields, n_points), dtype=dtype)
+        for i, a in enumerate(arrays):
+            a = np.asarray(a).reshape(-1)
+            if a.size != n_points:
+                raise ValueError(f"field {i} has {a.size} points, expected {n_points}")
+            host[i] = a
+        fm = torch.from_numpy(host).cuda()
+        ld = round_up(n_fields, 4)
+        pm = torch.zeros((n_points, ld), dtype=fm.dtype, device=fm.device)
+        transpose(fm, out=pm)
+        return cls(pm, n_fields)
+
+    def to_host_fields(self) -> np.ndarray:
+        """→ numpy [n_fields, n_points] (field-major)."""
+        torch = _torch()
+        fm = torch.empty((self.n_fields, self.n_points), dtype=self.data.dtype, device=self.data.device)
+        call("at_transpose", _ptr(self.data), self.n_points, self.n_fields, self.data.stride(0), _ptr(fm), fm.stride(0), self.data.element_size(), stream_ptr())
+        return fm.cpu().numpy()
+
+
+class HostPipeline:
+    """Streaming regrid of host-resident fields (at_pipeline_*)."""
+
+    def __init__(self, csr: CsrMatrix, chunk_fields: int = 128):
+        require_cuda()
+        self.csr = csr
+        h = c_void_p()
+        call("at_pipeline_create", csr.handle, int(chunk_fields), byref(h))
+        self._h = h
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            call("at_pipeline_destroy", self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def regrid(self, fields_in: Sequence[np.ndarray], fields_out: Sequence[np.ndarray] | None = None) -> list[np.ndarray]:
+        n = len(fields_in)
+        n_src, n_tgt = self.csr.shape[1], self.csr.shape[0]
+        ins = []
+        for i, a in enumerate(fields_in):
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+            if a.size != n_src:
+                raise ValueError(f"field {i} has {a.size} points, matrix expects {n_src}")
+            ins.append(a)
+        if fields_out is None:
+            fields_out = [np.empty((n_tgt,), dtype=np.float32) for _ in range(n)]
+        for i, a in enumerate(fields_out):
+            if a.dtype != np.float32 or a.size != n_tgt or not a.flags.c_contiguous:
+                raise ValueError(f"output field {i} must be contiguous float32[{n_tgt}]")
+        in_ptrs = (c_void_p * n)(*[a.ctypes.data for a in ins])
+        out_ptrs = (c_void_p * n)(*[a.ctypes.data for a in fields_out])
+        call("at_pipeline_regrid", self._h, in_ptrs, out_ptrs, n)
+        return list(fields_out)

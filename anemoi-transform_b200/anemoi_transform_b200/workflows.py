@@ -1,0 +1,39 @@
+"""Workflow / Pipeline — reference `workflow.py:17-43`, `workflows/pipeline.py:18-65`."""
+
+from __future__ import annotations
+
+from typing import Any, Iterator
+
+from .registry import Registry
+from .transform import Transform
+
+workflow_registry = Registry(__name__)
+
+
+class Workflow(Transform):
+    def __iter__(self) -> Iterator[Any]:
+        return iter(self(None))
+
+    def __call__(self, data: Any) -> Any:
+        return self.forward(data)
+
+
+@workflow_registry.register("pipeline")
+class Pipeline(Workflow):
+    """`a | b | c`: forward applies the filters in order, backward in reverse order."""
+
+    def __init__(self, *, filters: list[Any]) -> None:
+        self.filters = filters
+
+    def forward(self, data: Any) -> Any:
+        for f in self.filters:
+            data = f.forward(data)
+        return data
+
+    def backward(self, data: Any) -> Any:
+        for f in reversed(self.filters):
+            data = f.backward(data)
+        return data
+
+    def __repr__(self) -> str:
+        return f"Pipeline({self.filters})"

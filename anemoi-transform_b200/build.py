@@ -1,0 +1,97 @@
+"""Build libat_b200.so (the C-ABI CUDA library) in-tree for sm_100a.
+
+    python anemoi-transform_b200/build.py [--force] [--verbose]
+
+Objects and the shared library are written next to the Python package
+(anemoi_transform_b200/lib/) so the built .so travels with a snapshot of the repo.
+"""
+
+from __future__ import annotations
+
+import argparse
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent
+CSRC = HERE / "csrc"
+INCLUDE = ROOT / "include"
+LIB_DIR = HERE / "anemoi_transform_b200" / "lib"
+LIB_PATH = LIB_DIR / "libat_b200.so"
+
+SOURCES = ["misc.cu", "spmm.cu", "layout.cu", "knn.cu", "masks.cu", "pipeline.cu"]
+
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-lineinfo",
+    "-O3",
+    "-std=c++17",
+    # numpy / scipy never contract a*b+c; the kernels that need FMA ask for it explicitly
+    "-fmad=false",
+    "-Xcompiler",
+    "-fPIC",
+    "-Xcompiler",
+    "-fvisibility=hidden",
+    f"-I{INCLUDE}",
+    f"-I{CSRC}",
+]
+
+
+def _nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found; libat_b200.so cannot be built")
+    return nvcc
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE / "at_b200.h"]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    LIB_DIR.mkdir(parents=True, exist_ok=True)
+    stamp = LIB_DIR / "build.stamp"
+    fp = _fingerprint()
+    if not force and LIB_PATH.exists() and stamp.exists() and stamp.read_text() == fp:
+        return LIB_PATH
+    nvcc = _nvcc()
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src: str) -> Path:
+        obj = LIB_DIR / (Path(src).stem + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(CSRC / src), "-o", str(obj)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            sys.stderr.write(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}\n")
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB_PATH), *map(str, objs)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("linking libat_b200.so failed")
+    stamp.write_text(fp)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))

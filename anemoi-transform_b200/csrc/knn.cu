@@ -1,0 +1,751 @@
+// knn.cu — bucketed nearest-neighbour search on float64 xyz, replacing scipy's cKDTree on
+// the spatial path (reference src/anemoi/transform/spatial.py:96, 396, 501, 533, 628-632).
+//
+// Structure:
+//   - a hierarchy of uniform 3-D grids; level l has cell edge h0·2^l and its cell
+//     coordinates are the level-0 integer coordinates shifted right by l (exact nesting);
+//   - each level is a counting-sort bucket table keyed by hash(cell) & (M_l - 1)
+//     (no stored keys: colliding cells simply share a bucket — candidates are filtered by
+//     their true distance, so collisions cost time, never correctness);
+//   - a last pseudo-level has one bucket holding every point (brute force) so the search
+//     always terminates, e.g. for queries far outside the source domain;
+//   - one warp per query: 27 lanes look up the ring-1 buckets of the query's cell, duplicate
+//     buckets are dropped with __match_any_sync, the candidate ranges are flattened with a
+//     warp scan and all 32 lanes stride over the candidates; the k nearest are extracted by
+//     k successive warp-shuffle min-reductions on the key (d², index) — ties break to the
+//     lowest index — and the search moves to a coarser level until the k-th d² is inside
+//     the radius the ring is guaranteed to cover, (1-1e-8)·h_l.
+//
+// Exactness: d² = ((dx·dx)+(dy·dy))+(dz·dz) in float64 with __dmul_rn/__dadd_rn (no FMA
+// contraction), bitwise what cKDTree's sqeuclidean_distance_double gives for 3-vectors;
+// returned distance = sqrt(d²) (correctly rounded on both sides).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+namespace at {
+
+constexpr int kMaxLevels = 28;
+constexpr int kMaxK = 32;
+constexpr double kRingSafety = 1.0 - 1e-8;
+
+struct KnnLevel {
+    const int32_t* start;  // bucket offsets, mask + 2 entries
+    const int32_t* perm;   // source index per slot (nullptr: identity, brute-force level)
+    uint32_t mask;         // bucket count - 1
+    int shift;             // cell coordinate shift (level index); < 0 for the brute-force level
+    double cover2;         // (kRingSafety · h_l)²: every source closer than this was scanned
+};
+
+struct KnnDev {
+    const double *x, *y, *z;     // sources, original order
+    const double *sx, *sy, *sz;  // sources in level-0 slot order (coalesced candidate reads)
+    long long n;
+    double ox, oy, oz;  // grid origin
+    double inv_h0;
+    int n_levels;       // including the brute-force level
+    KnnLevel lv[kMaxLevels];
+};
+
+__device__ __forceinline__ uint32_t cell_hash(int cx, int cy, int cz) {
+    uint32_t h = static_cast<uint32_t>(cx) * 73856093u ^ static_cast<uint32_t>(cy) * 19349663u ^
+                 static_cast<uint32_t>(cz) * 83492791u;
+    h ^= h >> 16;
+    h *= 0x85ebca6bu;
+    h ^= h >> 13;
+    h *= 0xc2b2ae35u;
+    h ^= h >> 16;
+    return h;
+}
+
+__device__ __forceinline__ int cell_coord(double p, double origin, double inv_h) {
+    double t = floor(__dmul_rn(__dsub_rn(p, origin), inv_h));
+    t = fmin(fmax(t, -1073741824.0), 1073741823.0);
+    return static_cast<int>(t);
+}
+
+__device__ __forceinline__ double dist2(double qx, double qy, double qz, double px, double py, double pz) {
+    const double dx = __dsub_rn(px, qx), dy = __dsub_rn(py, qy), dz = __dsub_rn(pz, qz);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// ---- build ---------------------------------------------------------------------------
+__global__ void bbox_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                            const double* __restrict__ z, long long n, double* __restrict__ out6) {
+    // out6 = {minx, miny, minz, maxx, maxy, maxz}; atomics on ordered bit patterns.
+    double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double v[3] = {x[i], y[i], z[i]};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = fmin(mn[a], v[a]);
+            mx[a] = fmax(mx[a], v[a]);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fmin(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmax(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // order-preserving map double -> uint64
+        auto enc = [](double d) {
+            unsigned long long u = __double_as_longlong(d);
+            return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+        };
+        unsigned long long* o = reinterpret_cast<unsigned long long*>(out6);
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(o + a, enc(mn[a]));
+            atomicMax(o + 3 + a, enc(mx[a]));
+        }
+    }
+}
+
+// Occupancy of a coarse 64³ grid over the bounding box: estimates the area the points cover.
+__global__ void coarse_occupancy_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                        const double* __restrict__ z, long long n, double ox, double oy,
+                                        double oz, double inv_h, uint32_t* __restrict__ bits) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = min(63, max(0, cell_coord(x[i], ox, inv_h)));
+    const int cy = min(63, max(0, cell_coord(y[i], oy, inv_h)));
+    const int cz = min(63, max(0, cell_coord(z[i], oz, inv_h)));
+    const int c = (cz * 64 + cy) * 64 + cx;
+    atomicOr(bits + (c >> 5), 1u << (c & 31));
+}
+
+__global__ void popcount_kernel(const uint32_t* __restrict__ bits, int n_words, unsigned int* __restrict__ out) {
+    unsigned int c = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += gridDim.x * blockDim.x)
+        c += __popc(bits[i]);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void bucket_count_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                    const double* __restrict__ z, long long n, double ox, double oy,
+                                    double oz, double inv_h0, int shift, uint32_t mask,
+                                    int32_t* __restrict__ counts, int32_t* __restrict__ bucket_of) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = cell_coord(x[i], ox, inv_h0) >> shift;
+    const int cy = cell_coord(y[i], oy, inv_h0) >> shift;
+    const int cz = cell_coord(z[i], oz, inv_h0) >> shift;
+    const uint32_t b = cell_hash(cx, cy, cz) & mask;
+    bucket_of[i] = static_cast<int32_t>(b);
+    atomicAdd(counts + b, 1);
+}
+
+__global__ void bucket_scatter_kernel(const int32_t* __restrict__ bucket_of, long long n,
+                                      const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
+                                      int32_t* __restrict__ perm) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int b = bucket_of[i];
+    const int slot = atomicAdd(cursor + b, 1);
+    perm[start[b] + slot] = static_cast<int32_t>(i);
+}
+
+__global__ void permute_points_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                      const double* __restrict__ z, const int32_t* __restrict__ perm,
+                                      long long n, double* __restrict__ sx, double* __restrict__ sy,
+                                      double* __restrict__ sz) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = perm[i];
+    sx[i] = x[s];
+    sy[i] = y[s];
+    sz[i] = z[s];
+}
+
+// ---- exclusive scan of int32 (three small kernels) ---------------------------------------
+constexpr int kScanBlock = 1024;  // elements per block (256 threads x 4)
+
+__global__ void __launch_bounds__(256) scan_block_kernel(const int32_t* __restrict__ in, long long n,
+                                                         int32_t* __restrict__ out,
+                                                         int32_t* __restrict__ block_sums) {
+    __shared__ int warp_tot[8];
+    const long long base = static_cast<long long>(blockIdx.x) * kScanBlock + threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = base + j < n ? in[base + j] : 0;
+    const int t = v[0] + v[1] + v[2] + v[3];
+    int inc = t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+    for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+    int run = woff + inc - t;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (base + j < n) out[base + j] = run;
+        run += v[j];
+    }
+    if (threadIdx.x == 255) block_sums[blockIdx.x] = woff + inc;
+}
+
+// Single block: exclusive scan of the block sums in place (sequential chunks of 1024).
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int32_t* __restrict__ sums, int n_blocks,
+                                                         int32_t* __restrict__ total) {
+    __shared__ int warp_tot[32];
+    __shared__ int carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_blocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < n_blocks ? sums[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        int woff = 0;
+        for (int w = 0; w < warp; ++w) woff += warp_tot[w];
+        const int carry = carry_s;
+        if (i < n_blocks) sums[i] = carry + woff + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = carry + woff + inc;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total != nullptr) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(256) scan_add_kernel(int32_t* __restrict__ out, long long n,
+                                                       const int32_t* __restrict__ block_sums) {
+    const long long base = static_cast<long long>(blockIdx.x) * kScanBlock + threadIdx.x * 4;
+    const int off = block_sums[blockIdx.x];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (base + j < n) out[base + j] += off;
+}
+
+// out[0..n) = exclusive scan of in[0..n); out[n] = total.  scratch: ceil(n/1024) int32.
+static int exclusive_scan(const int32_t* in, long long n, int32_t* out, int32_t* scratch, cudaStream_t st) {
+    const long long blocks = (n + kScanBlock - 1) / kScanBlock;
+    if (blocks >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "scan too large");
+    scan_block_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(in, n, out, scratch);
+    AT_LAUNCH_CHECK("scan_block_kernel");
+    scan_sums_kernel<<<1, 1024, 0, st>>>(scratch, static_cast<int>(blocks), out + n);
+    AT_LAUNCH_CHECK("scan_sums_kernel");
+    scan_add_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(out, n, scratch);
+    AT_LAUNCH_CHECK("scan_add_kernel");
+    return AT_OK;
+}
+
+// ---- search --------------------------------------------------------------------------
+struct Cand {
+    double d2;
+    long long idx;
+};
+
+__device__ __forceinline__ bool key_less(double d2a, long long ia, double d2b, long long ib) {
+    return d2a < d2b || (d2a == d2b && ia < ib);
+}
+
+// Flattened ring-1 candidate ranges of one query at one level, held across the warp:
+// lane j owns range [s0, s0 + cnt) at flat offset `off`; `total` candidates in all.
+struct Ring {
+    int s0, cnt, off, total;
+};
+
+__device__ __forceinline__ Ring ring_ranges(const KnnDev& d, const KnnLevel& L, double qx, double qy,
+                                            double qz, int lane) {
+    Ring r;
+    r.s0 = 0;
+    r.cnt = 0;
+    if (L.shift < 0) {  // brute-force level: a single range over everything
+        if (lane == 0) r.cnt = static_cast<int>(d.n);
+    } else {
+        int b = -1 - lane;  // distinct dummy values for lanes >= 27
+        if (lane < 27) {
+            const int cx = (cell_coord(qx, d.ox, d.inv_h0) >> L.shift) + (lane % 3) - 1;
+            const int cy = (cell_coord(qy, d.oy, d.inv_h0) >> L.shift) + ((lane / 3) % 3) - 1;
+            const int cz = (cell_coord(qz, d.oz, d.inv_h0) >> L.shift) + (lane / 9) - 1;
+            b = static_cast<int>(cell_hash(cx, cy, cz) & L.mask);
+        }
+        const unsigned same = __match_any_sync(0xffffffffu, b);
+        const bool leader = lane < 27 && (__ffs(same) - 1) == lane;
+        if (leader) {
+            r.s0 = __ldg(L.start + b);
+            r.cnt = __ldg(L.start + b + 1) - r.s0;
+        }
+    }
+    int inc = r.cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    r.off = inc - r.cnt;
+    r.total = __shfl_sync(0xffffffffu, inc, 31);
+    return r;
+}
+
+// Slot of flat candidate t (t < total): binary search over the 32 lane offsets.
+__device__ __forceinline__ int ring_slot(const Ring& r, int t) {
+    // find the last lane whose off <= t and cnt > 0 covering t
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) {
+        const int probe = lo + step;
+        const int off_p = __shfl_sync(0xffffffffu, r.off, probe & 31);
+        if (probe < 32 && off_p <= t) lo = probe;
+    }
+    // lanes with cnt == 0 share the offset of the next non-empty lane; `lo` is the last lane
+    // with off <= t, and since offsets are non-decreasing the owner is the last such lane
+    // with cnt > 0 — which is `lo` itself unless trailing empty lanes follow the owner.
+    const int s0 = __shfl_sync(0xffffffffu, r.s0, lo);
+    const int off = __shfl_sync(0xffffffffu, r.off, lo);
+    const int cnt = __shfl_sync(0xffffffffu, r.cnt, lo);
+    return (t - off < cnt) ? s0 + (t - off) : -1;
+}
+
+// Load candidate at slot s of level L.
+__device__ __forceinline__ void load_cand(const KnnDev& d, const KnnLevel& L, bool level0, int s,
+                                          double& px, double& py, double& pz, long long& idx) {
+    if (L.perm == nullptr) {
+        idx = s;
+        px = d.x[s];
+        py = d.y[s];
+        pz = d.z[s];
+    } else {
+        idx = __ldg(L.perm + s);
+        if (level0) {
+            px = __ldg(d.sx + s);
+            py = __ldg(d.sy + s);
+            pz = __ldg(d.sz + s);
+        } else {
+            px = __ldg(d.x + idx);
+            py = __ldg(d.y + idx);
+            pz = __ldg(d.z + idx);
+        }
+    }
+}
+
+// One selection pass over the ring: smallest key strictly greater than (prev_d2, prev_idx)
+// with d2 < ub2.  Returns the warp-wide minimum (d2 = +inf when none).
+__device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, bool level0, const Ring& r,
+                                            double qx, double qy, double qz, double prev_d2,
+                                            long long prev_idx, double ub2, int lane) {
+    Cand best;
+    best.d2 = INFINITY;
+    best.idx = d.n;
+    // every lane runs the same number of iterations (ring_slot uses full-warp shuffles)
+    for (int t0 = 0; t0 < r.total; t0 += 32) {
+        const int t = t0 + lane;
+        const int s = ring_slot(r, t < r.total ? t : r.total - 1);
+        if (t < r.total && s >= 0) {
+            double px, py, pz;
+            long long idx;
+            load_cand(d, L, level0, s, px, py, pz, idx);
+            const double c2 = dist2(qx, qy, qz, px, py, pz);
+            if (c2 < ub2 && key_less(prev_d2, prev_idx, c2, idx) && key_less(c2, idx, best.d2, best.idx)) {
+                best.d2 = c2;
+                best.idx = idx;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best.d2, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, best.idx, o);
+        if (key_less(od, oi, best.d2, best.idx)) {
+            best.d2 = od;
+            best.idx = oi;
+        }
+    }
+    return best;
+}
+
+// Full k-NN of one query by one warp.  Lane j < k ends up holding the j-th neighbour.
+// Returns tie bits (valid when want_tie).
+__device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double qy, double qz, int k,
+                                            double ub2, bool want_tie, int lane, double& my_d2,
+                                            long long& my_idx) {
+    unsigned tie = 0;
+    for (int level = 0; level < d.n_levels; ++level) {
+        const KnnLevel& L = d.lv[level];
+        const bool last = level == d.n_levels - 1;
+        // A level whose ring cannot decide anything (cover radius below the best possible
+        // distance) is still scanned: cheap, and usually terminates at level 0.
+        const Ring r = ring_ranges(d, L, qx, qy, qz, lane);
+        my_d2 = INFINITY;
+        my_idx = d.n;
+        tie = 0;
+        if (r.total == 0 && !last && !(ub2 <= L.cover2)) continue;
+        double pd2 = -1.0;
+        long long pidx = -1;
+        int found = 0;
+        for (int j = 0; j < k; ++j) {
+            const Cand c = select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+            if (!(c.d2 < INFINITY)) break;
+            if (j > 0 && c.d2 == pd2) tie |= 1u;
+            if (lane == j) {
+                my_d2 = c.d2;
+                my_idx = c.idx;
+            }
+            pd2 = c.d2;
+            pidx = c.idx;
+            ++found;
+        }
+        const bool complete = found == k && pd2 < L.cover2;
+        if (complete || last || ub2 <= L.cover2) {
+            if (want_tie && found == k) {
+                const Cand c = select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+                if (c.d2 == pd2) tie |= 2u;
+            }
+            return tie;
+        }
+    }
+    return tie;
+}
+
+__global__ void __launch_bounds__(256)
+    knn_query_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
+                     const double* __restrict__ qz, long long nq, int k, double ub2,
+                     long long* __restrict__ idx_out, double* __restrict__ dist_out,
+                     uint8_t* __restrict__ tie_out) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
+        const double x = qx[q], y = qy[q], z = qz[q];
+        double d2;
+        long long idx;
+        const unsigned tie = knn_one(d, x, y, z, k, ub2, tie_out != nullptr, lane, d2, idx);
+        if (lane < k) {
+            idx_out[q * k + lane] = idx;
+            if (dist_out != nullptr) dist_out[q * k + lane] = sqrt(d2);
+        }
+        if (tie_out != nullptr && lane == 0) tie_out[q] = static_cast<uint8_t>(tie);
+    }
+}
+
+// min over sources of the distance to the 2nd nearest source (k = 2 self query).
+__global__ void __launch_bounds__(256)
+    min_second_nn_kernel(const KnnDev d, unsigned long long* __restrict__ out_bits) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    double best = INFINITY;
+    for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < d.n; q += warps) {
+        double d2;
+        long long idx;
+        knn_one(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d2, idx);
+        const double second = __shfl_sync(0xffffffffu, d2, 1);
+        best = fmin(best, second);
+    }
+    if (lane == 0) {
+        const double dist = sqrt(best);  // monotone: min of sqrt == sqrt of min
+        atomicMin(out_bits, static_cast<unsigned long long>(__double_as_longlong(dist)));
+    }
+}
+
+// Ball union: mark every source within r of any query.
+__global__ void __launch_bounds__(256)
+    ball_mark_kernel(const KnnDev d, int level, const double* __restrict__ qx,
+                     const double* __restrict__ qy, const double* __restrict__ qz, long long nq, double r2,
+                     uint8_t* __restrict__ mark) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const KnnLevel& L = d.lv[level];
+    for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
+        const double x = qx[q], y = qy[q], z = qz[q];
+        const Ring r = ring_ranges(d, L, x, y, z, lane);
+        for (int t0 = 0; t0 < r.total; t0 += 32) {
+            const int t = t0 + lane;
+            const int s = ring_slot(r, t < r.total ? t : r.total - 1);
+            if (t < r.total && s >= 0) {
+                double px, py, pz;
+                long long idx;
+                load_cand(d, L, level == 0, s, px, py, pz, idx);
+                if (dist2(x, y, z, px, py, pz) <= r2) mark[idx] = 1;
+            }
+        }
+    }
+}
+
+}  // namespace at
+
+struct at_knn {
+    long long n = 0;
+    int device = 0;
+    double h0 = 0;
+    double* d_x = nullptr;
+    double* d_y = nullptr;
+    double* d_z = nullptr;
+    double* d_sx = nullptr;
+    double* d_sy = nullptr;
+    double* d_sz = nullptr;
+    std::vector<void*> owned;  // every device allocation, for destroy
+    at::KnnDev dev;
+};
+
+using namespace at;
+
+namespace {
+
+int dev_alloc(at_knn* k, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes > 0 ? bytes : 16);
+    if (e != cudaSuccess)
+        return set_error(e == cudaErrorMemoryAllocation ? AT_ERR_NOMEM : AT_ERR_CUDA,
+                         "at_knn_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    k->owned.push_back(*p);
+    return AT_OK;
+}
+
+double dec_ordered(unsigned long long u) {
+    u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    memcpy(&d, &u, 8);
+    return d;
+}
+
+}  // namespace
+
+extern "C" int at_knn_destroy(at_knn_t* k) {
+    if (k == nullptr) return AT_OK;
+    for (void* p : k->owned) cudaFree(p);
+    delete k;
+    return AT_OK;
+}
+
+extern "C" int at_knn_create(const double* x, const double* y, const double* z, int64_t n, int on_device,
+                             double cell_size, at_knn_t** out) {
+    AT_REQUIRE(out != nullptr, "at_knn_create: out is null");
+    *out = nullptr;
+    AT_REQUIRE(x != nullptr && y != nullptr && z != nullptr, "at_knn_create: null coordinates");
+    AT_REQUIRE(n >= 1 && n < (1ll << 31) - 64, "at_knn_create: need 1 <= n < 2^31 (n=%lld)", (long long)n);
+
+    at_knn* k = new at_knn();
+    k->n = n;
+    cudaGetDevice(&k->device);
+    int rc = AT_OK;
+#define KNN_TRY(expr)             \
+    do {                          \
+        rc = (expr);              \
+        if (rc != AT_OK) {        \
+            at_knn_destroy(k);    \
+            return rc;            \
+        }                         \
+    } while (0)
+#define KNN_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            at_knn_destroy(k);                                                                  \
+            return set_error(AT_ERR_CUDA, "at_knn_create: %s failed: %s", #expr, cudaGetErrorString(_e)); \
+        }                                                                                       \
+    } while (0)
+
+    const size_t nb = static_cast<size_t>(n) * 8;
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_x), nb));
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_y), nb));
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_z), nb));
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    KNN_CUDA(cudaMemcpy(k->d_x, x, nb, kind));
+    KNN_CUDA(cudaMemcpy(k->d_y, y, nb, kind));
+    KNN_CUDA(cudaMemcpy(k->d_z, z, nb, kind));
+
+    const unsigned pt_blocks = static_cast<unsigned>((n + 255) / 256);
+
+    // bounding box
+    double* d_box = nullptr;
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_box), 6 * 8));
+    {
+        unsigned long long init[6];
+        for (int a = 0; a < 3; ++a) {
+            init[a] = ~0ull;
+            init[3 + a] = 0ull;
+        }
+        KNN_CUDA(cudaMemcpy(d_box, init, sizeof(init), cudaMemcpyHostToDevice));
+        bbox_kernel<<<std::min(pt_blocks, 1024u), 256>>>(k->d_x, k->d_y, k->d_z, n, d_box);
+        KNN_CUDA(cudaGetLastError());
+        KNN_CUDA(cudaMemcpy(init, d_box, sizeof(init), cudaMemcpyDeviceToHost));
+        double mn[3], mx[3];
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = dec_ordered(init[a]);
+            mx[a] = dec_ordered(init[3 + a]);
+            if (!std::isfinite(mn[a]) || !std::isfinite(mx[a])) {
+                at_knn_destroy(k);
+                return set_error(AT_ERR_INVALID, "at_knn_create: coordinates must be finite");
+            }
+        }
+        const double extent = std::max({mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2], 1e-300});
+        k->dev.ox = mn[0];
+        k->dev.oy = mn[1];
+        k->dev.oz = mn[2];
+
+        double h0 = cell_size;
+        if (!(h0 > 0)) {
+            // Estimate the covered surface from the occupancy of a coarse 64³ grid: points of a
+            // grid on a sphere fill ~area / hc² coarse cells; spacing ≈ sqrt(area / n).
+            uint32_t* d_bits = nullptr;
+            unsigned int* d_cnt = nullptr;
+            const int n_words = 64 * 64 * 64 / 32;
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_bits), n_words * 4));
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_cnt), 4));
+            KNN_CUDA(cudaMemset(d_bits, 0, n_words * 4));
+            KNN_CUDA(cudaMemset(d_cnt, 0, 4));
+            const double hc = extent / 64.0 * (1.0 + 1e-9);
+            coarse_occupancy_kernel<<<pt_blocks, 256>>>(k->d_x, k->d_y, k->d_z, n, mn[0], mn[1], mn[2],
+                                                       1.0 / hc, d_bits);
+            KNN_CUDA(cudaGetLastError());
+            popcount_kernel<<<32, 256>>>(d_bits, n_words, d_cnt);
+            KNN_CUDA(cudaGetLastError());
+            unsigned int occ = 0;
+            KNN_CUDA(cudaMemcpy(&occ, d_cnt, 4, cudaMemcpyDeviceToHost));
+            // A surface crossing a cubic lattice occupies ~1.5 cells per hc² of area.
+            const double area = std::max(1.0, static_cast<double>(occ)) * hc * hc / 1.5;
+            const double spacing = std::sqrt(area / static_cast<double>(n));
+            h0 = 2.0 * spacing;
+        }
+        h0 = std::max(h0, extent / 1.0e6);  // keeps level-0 integer coordinates small
+        h0 = std::max(h0, 1e-300);
+        k->h0 = h0;
+        k->dev.inv_h0 = 1.0 / h0;
+
+        // levels until one cell spans the whole bounding box, then the brute-force level
+        int n_grid = 1;
+        while (h0 * std::ldexp(1.0, n_grid - 1) < extent * 2.0 && n_grid < kMaxLevels - 1) ++n_grid;
+        k->dev.n_levels = n_grid + 1;
+    }
+
+    // sorted copies for level 0
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_sx), nb));
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_sy), nb));
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_sz), nb));
+
+    // bucket tables
+    uint32_t m0 = 1024;
+    while (m0 < static_cast<uint64_t>(n) && m0 < (1u << 26)) m0 <<= 1;
+    int32_t* d_bucket_of = nullptr;
+    int32_t* d_counts = nullptr;
+    int32_t* d_scratch = nullptr;
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_bucket_of), static_cast<size_t>(n) * 4));
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_counts), (static_cast<size_t>(m0) + 2) * 4));
+    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_scratch), (static_cast<size_t>(m0) / kScanBlock + 2) * 4));
+
+    const int n_grid = k->dev.n_levels - 1;
+    for (int l = 0; l < n_grid; ++l) {
+        uint32_t m = m0 >> std::min(2 * l, 30);
+        m = std::max(m, 256u);
+        int32_t* d_start = nullptr;
+        int32_t* d_perm = nullptr;
+        KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_start), (static_cast<size_t>(m) + 2) * 4));
+        KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_perm), static_cast<size_t>(n) * 4));
+        KNN_CUDA(cudaMemset(d_counts, 0, (static_cast<size_t>(m) + 2) * 4));
+        bucket_count_kernel<<<pt_blocks, 256>>>(k->d_x, k->d_y, k->d_z, n, k->dev.ox, k->dev.oy, k->dev.oz,
+                                               k->dev.inv_h0, l, m - 1, d_counts, d_bucket_of);
+        KNN_CUDA(cudaGetLastError());
+        KNN_TRY(exclusive_scan(d_counts, m, d_start, d_scratch, nullptr));
+        KNN_CUDA(cudaMemset(d_counts, 0, (static_cast<size_t>(m) + 2) * 4));
+        bucket_scatter_kernel<<<pt_blocks, 256>>>(d_bucket_of, n, d_start, d_counts, d_perm);
+        KNN_CUDA(cudaGetLastError());
+        if (l == 0) {
+            permute_points_kernel<<<pt_blocks, 256>>>(k->d_x, k->d_y, k->d_z, d_perm, n, k->d_sx, k->d_sy,
+                                                     k->d_sz);
+            KNN_CUDA(cudaGetLastError());
+        }
+        KnnLevel& L = k->dev.lv[l];
+        L.start = d_start;
+        L.perm = d_perm;
+        L.mask = m - 1;
+        L.shift = l;
+        const double cover = kRingSafety * k->h0 * std::ldexp(1.0, l);
+        L.cover2 = cover * cover;
+    }
+    {
+        KnnLevel& L = k->dev.lv[n_grid];
+        L.start = nullptr;
+        L.perm = nullptr;
+        L.mask = 0;
+        L.shift = -1;
+        L.cover2 = INFINITY;
+    }
+    k->dev.x = k->d_x;
+    k->dev.y = k->d_y;
+    k->dev.z = k->d_z;
+    k->dev.sx = k->d_sx;
+    k->dev.sy = k->d_sy;
+    k->dev.sz = k->d_sz;
+    k->dev.n = n;
+    KNN_CUDA(cudaDeviceSynchronize());
+#undef KNN_TRY
+#undef KNN_CUDA
+    *out = k;
+    return AT_OK;
+}
+
+static unsigned query_blocks(long long nq) {
+    const long long want = (nq + 7) / 8;  // 8 warps per block
+    const long long cap = static_cast<long long>(sm_count()) * 64;
+    return static_cast<unsigned>(std::max(1ll, std::min(want, cap)));
+}
+
+extern "C" int at_knn_query(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
+                            int64_t nq, int kk, double upper_bound, int64_t* idx_out, double* dist_out,
+                            uint8_t* tie_out, void* stream) {
+    AT_REQUIRE(k != nullptr && qx != nullptr && qy != nullptr && qz != nullptr && idx_out != nullptr,
+               "at_knn_query: null argument");
+    AT_REQUIRE(kk >= 1 && kk <= kMaxK, "at_knn_query: k must be in [1, %d] (k=%d)", kMaxK, kk);
+    AT_REQUIRE(nq >= 0, "at_knn_query: negative query count");
+    AT_REQUIRE(!(upper_bound != upper_bound) && upper_bound >= 0, "at_knn_query: bad distance_upper_bound");
+    if (nq == 0) return AT_OK;
+    const double ub2 = upper_bound * upper_bound;
+    knn_query_kernel<<<query_blocks(nq), 256, 0, as_stream(stream)>>>(
+        k->dev, qx, qy, qz, nq, kk, ub2, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+    AT_LAUNCH_CHECK("knn_query_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_ball_mark(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
+                            int64_t nq, double r, uint8_t* mark, void* stream) {
+    AT_REQUIRE(k != nullptr && qx != nullptr && qy != nullptr && qz != nullptr && mark != nullptr,
+               "at_ball_mark: null argument");
+    AT_REQUIRE(nq >= 0 && r >= 0, "at_ball_mark: bad arguments");
+    if (nq == 0) return AT_OK;
+    const double r2 = r * r;
+    int level = k->dev.n_levels - 1;
+    for (int l = 0; l < k->dev.n_levels; ++l) {
+        if (r2 < k->dev.lv[l].cover2) {
+            level = l;
+            break;
+        }
+    }
+    ball_mark_kernel<<<query_blocks(nq), 256, 0, as_stream(stream)>>>(k->dev, level, qx, qy, qz, nq, r2, mark);
+    AT_LAUNCH_CHECK("ball_mark_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_min_nn_distance(const at_knn_t* k, double* out_host, void* stream) {
+    AT_REQUIRE(k != nullptr && out_host != nullptr, "at_min_nn_distance: null argument");
+    unsigned long long* d_bits = nullptr;
+    AT_CUDA_TRY(cudaMalloc(&d_bits, 8));
+    const double inf = INFINITY;
+    unsigned long long init;
+    memcpy(&init, &inf, 8);
+    cudaStream_t st = as_stream(stream);
+    cudaError_t e = cudaMemcpyAsync(d_bits, &init, 8, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        min_second_nn_kernel<<<query_blocks(k->n), 256, 0, st>>>(k->dev, d_bits);
+        e = cudaGetLastError();
+    }
+    unsigned long long bits = init;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&bits, d_bits, 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_bits);
+    if (e != cudaSuccess) return set_error(AT_ERR_CUDA, "at_min_nn_distance: %s", cudaGetErrorString(e));
+    memcpy(out_host, &bits, 8);
+    return AT_OK;
+}

@@ -1,0 +1,162 @@
+// layout.cu — layout changes around the SpMM: field-major <-> point-major transposes, the
+// row gather of the nearest-neighbour / masked regrid, and mask construction by comparison.
+//
+// Reference call sites (src/anemoi/transform/filters/fields/):
+//   regrid.py:309  `field.to_numpy(flatten=True)` delivers one array per field (field-major);
+//   regrid.py:380  `data[..., self.nearest_grid_points]`  (ScipyKDTreeNearestNeighbours)
+//   regrid.py:420  `data[..., self.mask]`                  (MaskedRegrid)
+//   apply_mask.py:160-163  `OPERATORS[op](mask_values, threshold)` / `mask_values == mask_value`
+#include "common.cuh"
+
+namespace at {
+
+constexpr int kTile = 64;  // transpose tile edge (elements)
+
+// dst[c, r] = src[r, c].  64x64 tile through shared memory; 256 threads, each moves 16
+// elements.  Reads and writes are both coalesced along their contiguous dimension.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    transpose_kernel(const T* __restrict__ src, long long rows, long long cols, size_t ld_src,
+                     T* __restrict__ dst, size_t ld_dst, long long tiles_c) {
+    __shared__ T tile[kTile][kTile + 1];
+    const long long tr = blockIdx.x / tiles_c, tc = blockIdx.x % tiles_c;
+    const long long r0 = tr * kTile, c0 = tc * kTile;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+#pragma unroll 4
+    for (int i = ty; i < kTile; i += 4) {
+        const long long r = r0 + i, c = c0 + tx;
+        if (r < rows && c < cols) tile[i][tx] = __ldg(src + static_cast<size_t>(r) * ld_src + c);
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int i = ty; i < kTile; i += 4) {
+        const long long c = c0 + i, r = r0 + tx;
+        if (r < rows && c < cols) dst[static_cast<size_t>(c) * ld_dst + r] = tile[tx][i];
+    }
+}
+
+// One warp per output row and 16-byte chunk tile.
+template <typename V>
+__global__ void __launch_bounds__(256)
+    gather_rows_kernel(const long long* __restrict__ idx, long long n_out, long long n_src,
+                       const V* __restrict__ X, size_t ldx, V* __restrict__ Y, size_t ldy,
+                       int n_vec, int* __restrict__ err_flag) {
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n_out) return;
+    const int lane = threadIdx.x & 31;
+    const long long s = idx[row];
+    if (s < 0 || s >= n_src) {
+        if (lane == 0 && err_flag != nullptr) *err_flag = 1;
+        return;
+    }
+    const V* xr = X + static_cast<size_t>(s) * ldx;
+    V* yr = Y + static_cast<size_t>(row) * ldy;
+    const int v0 = blockIdx.y * 128;
+    V tmp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int v = v0 + j * 32 + lane;
+        if (v < n_vec) tmp[j] = __ldg(xr + v);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int v = v0 + j * 32 + lane;
+        if (v < n_vec) __stcs(yr + v, tmp[j]);
+    }
+}
+
+__global__ void compare_mask_kernel(const float* __restrict__ values, size_t stride, long long n,
+                                    int op, float thr, uint8_t* __restrict__ mask) {
+    const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = values[static_cast<size_t>(i) * stride];
+    bool m;
+    switch (op) {
+        case 0: m = v == thr; break;
+        case 1: m = v != thr; break;
+        case 2: m = v > thr; break;
+        case 3: m = v >= thr; break;
+        case 4: m = v < thr; break;
+        default: m = v <= thr; break;
+    }
+    mask[i] = m ? 1 : 0;
+}
+
+template <typename T>
+static int launch_transpose(const void* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst,
+                            int64_t ld_dst, cudaStream_t st) {
+    const long long tiles_r = (rows + kTile - 1) / kTile, tiles_c = (cols + kTile - 1) / kTile;
+    const long long n_tiles = tiles_r * tiles_c;
+    if (n_tiles >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_transpose: array too large");
+    transpose_kernel<T><<<static_cast<unsigned>(n_tiles), 256, 0, st>>>(
+        static_cast<const T*>(src), rows, cols, static_cast<size_t>(ld_src), static_cast<T*>(dst),
+        static_cast<size_t>(ld_dst), tiles_c);
+    AT_LAUNCH_CHECK("transpose_kernel");
+    return AT_OK;
+}
+
+template <typename V>
+static int launch_gather(const int64_t* idx, int64_t n_out, int64_t n_src, const void* X, int64_t ldx_v,
+                         void* Y, int64_t ldy_v, int64_t n_vec, int32_t* err_flag, cudaStream_t st) {
+    const int64_t gx = (n_out + 7) / 8, gy = (n_vec + 127) / 128;
+    if (gx >= (1ll << 31) || gy > 65535) return set_error(AT_ERR_UNSUPPORTED, "at_gather_rows: too large");
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
+    gather_rows_kernel<V><<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(idx), n_out, n_src,
+                                               static_cast<const V*>(X), static_cast<size_t>(ldx_v),
+                                               static_cast<V*>(Y), static_cast<size_t>(ldy_v),
+                                               static_cast<int>(n_vec), err_flag);
+    AT_LAUNCH_CHECK("gather_rows_kernel");
+    return AT_OK;
+}
+
+}  // namespace at
+
+using namespace at;
+
+extern "C" int at_transpose(const void* src, int64_t rows, int64_t cols, int64_t ld_src, void* dst,
+                            int64_t ld_dst, int elem_size, void* stream) {
+    AT_REQUIRE(src != nullptr && dst != nullptr, "at_transpose: null argument");
+    AT_REQUIRE(rows >= 0 && cols >= 0 && ld_src >= cols && ld_dst >= rows,
+               "at_transpose: bad shape rows=%lld cols=%lld ld_src=%lld ld_dst=%lld", (long long)rows,
+               (long long)cols, (long long)ld_src, (long long)ld_dst);
+    if (rows == 0 || cols == 0) return AT_OK;
+    if (elem_size == 4) return launch_transpose<float>(src, rows, cols, ld_src, dst, ld_dst, as_stream(stream));
+    if (elem_size == 8) return launch_transpose<double>(src, rows, cols, ld_src, dst, ld_dst, as_stream(stream));
+    return set_error(AT_ERR_INVALID, "at_transpose: elem_size must be 4 or 8");
+}
+
+extern "C" int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src, const void* X,
+                              int64_t ldx, void* Y, int64_t ldy, int64_t n_fields, int elem_size,
+                              int32_t* err_flag, void* stream) {
+    AT_REQUIRE(idx != nullptr && X != nullptr && Y != nullptr, "at_gather_rows: null argument");
+    AT_REQUIRE(elem_size == 4 || elem_size == 8, "at_gather_rows: elem_size must be 4 or 8");
+    AT_REQUIRE(n_out >= 0 && n_src >= 0 && n_fields >= 0 && ldx >= n_fields && ldy >= n_fields,
+               "at_gather_rows: bad shape");
+    if (n_out == 0 || n_fields == 0) return AT_OK;
+    cudaStream_t st = as_stream(stream);
+    const int64_t per16 = 16 / elem_size;
+    const bool vec16 = ldx % per16 == 0 && ldy % per16 == 0 &&
+                       (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0;
+    if (vec16) {
+        // whole 16-byte chunks, including the padding columns inside ld
+        const int64_t n_vec = (n_fields + per16 - 1) / per16;
+        return launch_gather<uint4>(idx, n_out, n_src, X, ldx / per16, Y, ldy / per16, n_vec, err_flag, st);
+    }
+    if (elem_size == 4)
+        return launch_gather<uint32_t>(idx, n_out, n_src, X, ldx, Y, ldy, n_fields, err_flag, st);
+    return launch_gather<uint2>(idx, n_out, n_src, X, ldx, Y, ldy, n_fields, err_flag, st);
+}
+
+extern "C" int at_compare_mask(const float* values, int64_t stride, int64_t n, int op, float threshold,
+                               uint8_t* mask, void* stream) {
+    AT_REQUIRE(values != nullptr && mask != nullptr, "at_compare_mask: null argument");
+    AT_REQUIRE(op >= 0 && op <= 5, "at_compare_mask: unknown operator %d", op);
+    AT_REQUIRE(n >= 0 && stride >= 1, "at_compare_mask: bad shape");
+    if (n == 0) return AT_OK;
+    const int64_t blocks = (n + 255) / 256;
+    AT_REQUIRE(blocks < (1ll << 31), "at_compare_mask: too large");
+    compare_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+        values, static_cast<size_t>(stride), n, op, threshold, mask);
+    AT_LAUNCH_CHECK("compare_mask_kernel");
+    return AT_OK;
+}

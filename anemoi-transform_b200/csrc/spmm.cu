@@ -1,0 +1,702 @@
+// spmm.cu — the regrid hot loop: a CSR interpolation matrix staged once in HBM and applied
+// to a point-major batch of fields, Y[n_tgt, F] = A · X[n_src, F].
+//
+// Replaces scipy.sparse csr_matvec behind `self.matrix @ data`
+// (reference src/anemoi/transform/filters/fields/regrid.py:309-310), batched over the
+// per-field Python loop of RegridFilter._interpolate (regrid.py:204-208).
+//
+// Layout / mapping:
+//   - X, Y row-major [points, fields]; one nonzero's weight multiplies a contiguous row
+//     of fields, read as coalesced 16-byte vectors;
+//   - one warp per target row per column tile (32·VPL float4 = 128·VPL fields);
+//   - a CTA owns `rows_per_cta` consecutive target rows; their CSR segment (column indices
+//     and weights, contiguous in memory) is staged in shared memory once per CTA — with a
+//     1-D bulk async copy (TMA, cp.async.bulk + mbarrier) when the matrix has a uniform
+//     row length, so the tile is regular and 16-byte aligned, else with cooperative loads;
+//   - grid.x walks row blocks (fastest) so concurrently resident CTAs reference
+//     neighbouring source rows and the ~2x re-reference of each source row hits L2;
+//     grid.y walks column tiles, bounding the live source working set;
+//   - accumulation is scipy's, bit for bit: sequential in storage order from +0 with
+//     __fmul_rn / __fadd_rn (never contracted to FMA);
+//   - Y is write-once: streaming stores (st.global.cs).
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+
+struct at_csr {
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int data_dtype = AT_F32;
+    int uniform_nnz = 0;
+    int max_row_nnz = 0;
+    int32_t* d_indptr = nullptr;   // n_rows + 1 (+ padding)
+    int32_t* d_indices = nullptr;  // nnz (+ padding)
+    void* d_data = nullptr;        // nnz float or double (+ padding)
+    int device = 0;
+};
+
+namespace at {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / kWarp;
+constexpr int kMaxRowsPerCta = 64;
+constexpr int kSegCap = 1024;  // CSR entries staged per CTA (8 KB of smem)
+constexpr int kPad = 64;       // padding entries behind the device CSR arrays
+
+// ---- mbarrier / bulk-copy (TMA 1-D) primitives --------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+struct SpmmArgs {
+    const int32_t* __restrict__ indptr;
+    const int32_t* __restrict__ indices;
+    const float* __restrict__ data;
+    const float4* __restrict__ X;
+    float4* __restrict__ Y;
+    size_t ldx4, ldy4;  // leading dimensions in float4
+    int n_rows;
+    int n_vec;          // F / 4 (float4 columns), rounded up
+    int rows_per_cta;
+};
+
+__device__ __forceinline__ float4 mul_add_rn(float4 acc, float w, float4 x) {
+    acc.x = __fadd_rn(acc.x, __fmul_rn(w, x.x));
+    acc.y = __fadd_rn(acc.y, __fmul_rn(w, x.y));
+    acc.z = __fadd_rn(acc.z, __fmul_rn(w, x.z));
+    acc.w = __fadd_rn(acc.w, __fmul_rn(w, x.w));
+    return acc;
+}
+
+// Stage the CTA's CSR segment in shared memory.  Returns the base entry (segment start).
+// UNNZ > 0: uniform row length, regular tile -> bulk async copy when BULK.
+template <int UNNZ, bool BULK>
+__device__ __forceinline__ void stage_segment(const SpmmArgs& a, int r0, int nrows, int* s_ptr,
+                                              int* s_idx, float* s_w, uint64_t* s_bar,
+                                              int& seg_base, bool& in_smem) {
+    const int tid = threadIdx.x;
+    if (UNNZ > 0) {
+        seg_base = r0 * UNNZ;
+        const int len = nrows * UNNZ;
+        in_smem = true;  // host guarantees rows_per_cta * UNNZ <= kSegCap
+        if (BULK) {
+            // Regular tile: base is a multiple of 4 entries (rows_per_cta % 4 == 0), length is
+            // rounded up to 16 bytes (arrays are padded), so both copies are 16-byte aligned.
+            const uint32_t bytes = static_cast<uint32_t>((len * 4 + 15) & ~15);
+            if (tid == 0) {
+                mbar_init(s_bar, 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncthreads();
+            if (tid == 0) {
+                mbar_expect_tx(s_bar, 2 * bytes);
+                bulk_g2s(s_idx, a.indices + seg_base, bytes, s_bar);
+                bulk_g2s(s_w, a.data + seg_base, bytes, s_bar);
+            }
+            mbar_wait(s_bar, 0);
+        } else {
+            for (int i = tid; i < len; i += kThreads) {
+                s_idx[i] = __ldg(a.indices + seg_base + i);
+                s_w[i] = __ldg(a.data + seg_base + i);
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int i = tid; i <= nrows; i += kThreads) s_ptr[i] = __ldg(a.indptr + r0 + i);
+        __syncthreads();
+        seg_base = s_ptr[0];
+        const int len = s_ptr[nrows] - seg_base;
+        in_smem = len <= kSegCap;
+        if (in_smem) {
+            for (int i = tid; i < len; i += kThreads) {
+                s_idx[i] = __ldg(a.indices + seg_base + i);
+                s_w[i] = __ldg(a.data + seg_base + i);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Accumulate one target row for this lane's VPL float4 columns.
+// (p0, p1) are entry offsets relative to the staged segment when IN_SMEM, absolute otherwise.
+template <int VPL, int U, bool IN_SMEM>
+__device__ __forceinline__ void accumulate_row(const SpmmArgs& a, int p0, int p1,
+                                               const int* s_idx, const float* s_w,
+                                               const int (&vcol)[VPL], const bool (&vok)[VPL],
+                                               float4 (&acc)[VPL]) {
+    for (int p = p0; p < p1; p += U) {
+        int c[U];
+        float w[U];
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const bool ok = p + j < p1;
+            if (IN_SMEM) {
+                c[j] = ok ? s_idx[p + j] : 0;
+                w[j] = ok ? s_w[p + j] : 0.0f;
+            } else {
+                c[j] = ok ? __ldg(a.indices + p + j) : 0;
+                w[j] = ok ? __ldg(a.data + p + j) : 0.0f;
+            }
+        }
+        float4 x[U][VPL];
+        // Issue every gather of the chunk before the first dependent add.
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const float4* xr = a.X + static_cast<size_t>(c[j]) * a.ldx4;
+#pragma unroll
+            for (int v = 0; v < VPL; ++v)
+                if (vok[v] && p + j < p1) x[j][v] = ld_ro_f4(xr + vcol[v]);
+        }
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            if (p + j < p1) {
+#pragma unroll
+                for (int v = 0; v < VPL; ++v) acc[v] = mul_add_rn(acc[v], w[j], x[j][v]);
+            }
+        }
+    }
+}
+
+template <int VPL, int UNNZ, bool BULK>
+__global__ void __launch_bounds__(kThreads) spmm_f32_kernel(const SpmmArgs a) {
+    __shared__ __align__(16) int s_idx[kSegCap];
+    __shared__ __align__(16) float s_w[kSegCap];
+    __shared__ int s_ptr[kMaxRowsPerCta + 1];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int nrows = min(a.rows_per_cta, a.n_rows - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    int vcol[VPL];
+    bool vok[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+        vcol[v] = blockIdx.y * (kWarp * VPL) + v * kWarp + lane;
+        vok[v] = vcol[v] < a.n_vec;
+    }
+
+    int seg_base;
+    bool in_smem;
+    stage_segment<UNNZ, BULK>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
+
+    for (int lr = warp; lr < nrows; lr += kWarps) {
+        float4 acc[VPL];
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        if constexpr (UNNZ > 0) {
+            accumulate_row<VPL, (UNNZ < 4 ? UNNZ : 4), true>(a, lr * UNNZ, (lr + 1) * UNNZ, s_idx,
+                                                             s_w, vcol, vok, acc);
+        } else if (in_smem) {
+            accumulate_row<VPL, 4, true>(a, s_ptr[lr] - seg_base, s_ptr[lr + 1] - seg_base, s_idx,
+                                         s_w, vcol, vok, acc);
+        } else {
+            accumulate_row<VPL, 4, false>(a, s_ptr[lr], s_ptr[lr + 1], s_idx, s_w, vcol, vok, acc);
+        }
+
+        float4* yr = a.Y + static_cast<size_t>(r0 + lr) * a.ldy4;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v)
+            if (vok[v]) st_stream_f4(yr + vcol[v], acc[v]);
+    }
+}
+
+// ---- fused epilogue variant: general CSR, one float4 per lane, tile table ------------
+struct FusedArgs {
+    SpmmArgs s;
+    const EpiTile* __restrict__ tiles;
+    const ColF32* __restrict__ cols;
+    const uint8_t* __restrict__ row_mask;
+    float* __restrict__ Yf;
+    size_t ldy;  // in floats
+};
+
+__global__ void __launch_bounds__(kThreads) spmm_fused_kernel(const FusedArgs f) {
+    __shared__ __align__(16) int s_idx[kSegCap];
+    __shared__ __align__(16) float s_w[kSegCap];
+    __shared__ int s_ptr[kMaxRowsPerCta + 1];
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const SpmmArgs& a = f.s;
+    const int r0 = blockIdx.x * a.rows_per_cta;
+    const int nrows = min(a.rows_per_cta, a.n_rows - r0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const EpiTile tile = f.tiles[blockIdx.y];
+    int vcol[1] = {tile.in_vec0 + lane};
+    bool vok[1] = {lane < tile.n_vec};
+
+    int seg_base;
+    bool in_smem;
+    stage_segment<0, false>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
+
+    for (int lr = warp; lr < nrows; lr += kWarps) {
+        float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
+        if (in_smem) {
+            accumulate_row<1, 4, true>(a, s_ptr[lr] - seg_base, s_ptr[lr + 1] - seg_base, s_idx,
+                                       s_w, vcol, vok, acc);
+        } else {
+            accumulate_row<1, 4, false>(a, s_ptr[lr], s_ptr[lr + 1], s_idx, s_w, vcol, vok, acc);
+        }
+        const int row = r0 + lr;
+        const bool masked = f.row_mask != nullptr && f.row_mask[row] != 0;
+        if (vok[0])
+            epilogue_store<float>(tile, lane, acc[0].x, acc[0].y, acc[0].z, acc[0].w, f.cols, masked,
+                                  f.Yf + static_cast<size_t>(row) * f.ldy);
+    }
+}
+
+// ---- pointwise on a resident batch (identity "matrix") --------------------------------
+template <typename T>
+struct PointwiseArgs {
+    const EpiTile* __restrict__ tiles;
+    const typename ColStore<T>::type* __restrict__ cols;
+    const uint8_t* __restrict__ row_mask;
+    const T* __restrict__ X;
+    T* __restrict__ Y;
+    size_t ldx, ldy;
+    long long n_rows;
+    int rows_per_cta;
+};
+
+__device__ __forceinline__ void load4(const float* p, float& a, float& b, float& c, float& d) {
+    const float4 v = ld_ro_f4(reinterpret_cast<const float4*>(p));
+    a = v.x, b = v.y, c = v.z, d = v.w;
+}
+__device__ __forceinline__ void load4(const double* p, double& a, double& b, double& c, double& d) {
+    const double2 v0 = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 v1 = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    a = v0.x, b = v0.y, c = v1.x, d = v1.y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pointwise_kernel(const PointwiseArgs<T> f) {
+    const long long r0 = static_cast<long long>(blockIdx.x) * f.rows_per_cta;
+    const int nrows = static_cast<int>(min(static_cast<long long>(f.rows_per_cta), f.n_rows - r0));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const EpiTile tile = f.tiles[blockIdx.y];
+    if (lane >= tile.n_vec) return;
+    for (int lr = warp; lr < nrows; lr += kWarps) {
+        const long long row = r0 + lr;
+        T a0, a1, a2, a3;
+        load4(f.X + static_cast<size_t>(row) * f.ldx + 4 * static_cast<size_t>(tile.in_vec0 + lane), a0, a1, a2, a3);
+        const bool masked = f.row_mask != nullptr && f.row_mask[row] != 0;
+        epilogue_store<T>(tile, lane, a0, a1, a2, a3, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy);
+    }
+}
+
+// ---- generic dtypes (float64 matrix and / or float64 fields): scalar columns ----------
+template <typename TW, typename TX, typename TY>
+__global__ void __launch_bounds__(kThreads)
+    spmm_generic_kernel(const int32_t* __restrict__ indptr, const int32_t* __restrict__ indices,
+                        const TW* __restrict__ data, const TX* __restrict__ X, size_t ldx,
+                        TY* __restrict__ Y, size_t ldy, int n_rows, int n_fields) {
+    const int row = blockIdx.x * kWarps + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const int p0 = __ldg(indptr + row), p1 = __ldg(indptr + row + 1);
+    for (int col = blockIdx.y * 128 + lane; col < min(n_fields, (int)(blockIdx.y + 1) * 128);
+         col += kWarp) {
+        TY acc = TY(0);
+        for (int p = p0; p < p1; ++p) {
+            const TY w = static_cast<TY>(__ldg(data + p));
+            const TY x = static_cast<TY>(__ldg(X + static_cast<size_t>(__ldg(indices + p)) * ldx + col));
+            if (sizeof(TY) == 8)
+                acc = __dadd_rn(acc, __dmul_rn(w, x));
+            else
+                acc = __fadd_rn(acc, __fmul_rn(w, x));
+        }
+        Y[static_cast<size_t>(row) * ldy + col] = acc;
+    }
+}
+
+template <typename TW, typename TX, typename TY>
+static int launch_generic(const at_csr* csr, const void* X, int64_t ldx, void* Y, int64_t ldy,
+                          int64_t n_fields, cudaStream_t st) {
+    dim3 grid(static_cast<unsigned>((csr->n_rows + kWarps - 1) / kWarps),
+              static_cast<unsigned>((n_fields + 127) / 128));
+    spmm_generic_kernel<TW, TX, TY><<<grid, kThreads, 0, st>>>(
+        csr->d_indptr, csr->d_indices, static_cast<const TW*>(csr->d_data),
+        static_cast<const TX*>(X), static_cast<size_t>(ldx), static_cast<TY*>(Y),
+        static_cast<size_t>(ldy), static_cast<int>(csr->n_rows), static_cast<int>(n_fields));
+    AT_LAUNCH_CHECK("spmm_generic_kernel");
+    return AT_OK;
+}
+
+template <int VPL>
+static int launch_f32(const at_csr* csr, const SpmmArgs& args, bool bulk, bool force_general,
+                      cudaStream_t st) {
+    const unsigned gx = static_cast<unsigned>((csr->n_rows + args.rows_per_cta - 1) / args.rows_per_cta);
+    const unsigned gy = static_cast<unsigned>((args.n_vec + kWarp * VPL - 1) / (kWarp * VPL));
+    if (gy > 65535u) return set_error(AT_ERR_UNSUPPORTED, "too many column tiles (%u)", gy);
+    dim3 grid(gx, gy);
+    const bool uniform4 = !force_general && csr->uniform_nnz == 4;
+    if (uniform4 && bulk)
+        spmm_f32_kernel<VPL, 4, true><<<grid, kThreads, 0, st>>>(args);
+    else if (uniform4)
+        spmm_f32_kernel<VPL, 4, false><<<grid, kThreads, 0, st>>>(args);
+    else
+        spmm_f32_kernel<VPL, 0, false><<<grid, kThreads, 0, st>>>(args);
+    AT_LAUNCH_CHECK("spmm_f32_kernel");
+    return AT_OK;
+}
+
+template <typename T>
+static bool copy_index_array(const void* src, int dtype, int64_t n, std::vector<int32_t>& dst,
+                             int64_t limit, const char* what, bool monotone) {
+    dst.resize(static_cast<size_t>(n));
+    int64_t prev = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = dtype == AT_I32 ? static_cast<const int32_t*>(src)[i]
+                                          : static_cast<const int64_t*>(src)[i];
+        if (v < 0 || v > limit) {
+            set_error(AT_ERR_INVALID, "%s[%lld] = %lld out of range [0, %lld]", what,
+                      (long long)i, (long long)v, (long long)limit);
+            return false;
+        }
+        if (monotone && v < prev) {
+            set_error(AT_ERR_INVALID, "%s is not non-decreasing at %lld", what, (long long)i);
+            return false;
+        }
+        prev = v;
+        dst[static_cast<size_t>(i)] = static_cast<int32_t>(v);
+    }
+    return true;
+}
+
+}  // namespace at
+
+using namespace at;
+
+extern "C" int at_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const void* indptr,
+                             int indptr_dtype, const void* indices, int indices_dtype,
+                             const void* data, int data_dtype, at_csr_t** out) {
+    AT_REQUIRE(out != nullptr, "at_csr_create: out is null");
+    *out = nullptr;
+    AT_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "at_csr_create: negative size");
+    AT_REQUIRE(n_rows < (1ll << 31) - 64 && n_cols < (1ll << 31) && nnz < (1ll << 31) - 64,
+               "at_csr_create: sizes must be < 2^31 (n_rows=%lld n_cols=%lld nnz=%lld)",
+               (long long)n_rows, (long long)n_cols, (long long)nnz);
+    AT_REQUIRE(indptr != nullptr && (nnz == 0 || (indices != nullptr && data != nullptr)),
+               "at_csr_create: null array");
+    AT_REQUIRE((indptr_dtype == AT_I32 || indptr_dtype == AT_I64) &&
+                   (indices_dtype == AT_I32 || indices_dtype == AT_I64) &&
+                   (data_dtype == AT_F32 || data_dtype == AT_F64),
+               "at_csr_create: bad dtype code");
+
+    std::vector<int32_t> h_ptr, h_idx;
+    if (!copy_index_array<int32_t>(indptr, indptr_dtype, n_rows + 1, h_ptr, nnz, "indptr", true))
+        return AT_ERR_INVALID;
+    AT_REQUIRE(h_ptr[0] == 0 && h_ptr[static_cast<size_t>(n_rows)] == nnz,
+               "at_csr_create: indptr must start at 0 and end at nnz");
+    if (!copy_index_array<int32_t>(indices, indices_dtype, nnz, h_idx, n_cols - 1, "indices", false))
+        return AT_ERR_INVALID;
+
+    at_csr* c = new at_csr();
+    c->n_rows = n_rows;
+    c->n_cols = n_cols;
+    c->nnz = nnz;
+    c->data_dtype = data_dtype;
+    int uniform = n_rows > 0 ? h_ptr[1] - h_ptr[0] : 0, max_nnz = 0;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int len = h_ptr[static_cast<size_t>(r + 1)] - h_ptr[static_cast<size_t>(r)];
+        if (len != uniform) uniform = 0;
+        max_nnz = std::max(max_nnz, len);
+    }
+    c->uniform_nnz = uniform;
+    c->max_row_nnz = max_nnz;
+    cudaGetDevice(&c->device);
+
+    const size_t esz = data_dtype == AT_F32 ? 4 : 8;
+    auto fail = [&](int code) {
+        at_csr_destroy(c);
+        return code;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&c->d_indptr, (static_cast<size_t>(n_rows) + 1 + kPad) * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_indices, (static_cast<size_t>(nnz) + kPad) * 4)) != cudaSuccess ||
+        (e = cudaMalloc(&c->d_data, (static_cast<size_t>(nnz) + kPad) * esz)) != cudaSuccess) {
+        set_error(e == cudaErrorMemoryAllocation ? AT_ERR_NOMEM : AT_ERR_CUDA,
+                  "at_csr_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+        return fail(e == cudaErrorMemoryAllocation ? AT_ERR_NOMEM : AT_ERR_CUDA);
+    }
+    if ((e = cudaMemset(c->d_indptr, 0, (static_cast<size_t>(n_rows) + 1 + kPad) * 4)) != cudaSuccess ||
+        (e = cudaMemset(c->d_indices, 0, (static_cast<size_t>(nnz) + kPad) * 4)) != cudaSuccess ||
+        (e = cudaMemset(c->d_data, 0, (static_cast<size_t>(nnz) + kPad) * esz)) != cudaSuccess ||
+        (e = cudaMemcpy(c->d_indptr, h_ptr.data(), (static_cast<size_t>(n_rows) + 1) * 4,
+                        cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (nnz > 0 && (e = cudaMemcpy(c->d_indices, h_idx.data(), static_cast<size_t>(nnz) * 4,
+                                    cudaMemcpyHostToDevice)) != cudaSuccess) ||
+        (nnz > 0 && (e = cudaMemcpy(c->d_data, data, static_cast<size_t>(nnz) * esz,
+                                    cudaMemcpyHostToDevice)) != cudaSuccess)) {
+        set_error(AT_ERR_CUDA, "at_csr_create: staging the matrix failed: %s", cudaGetErrorString(e));
+        return fail(AT_ERR_CUDA);
+    }
+    *out = c;
+    return AT_OK;
+}
+
+extern "C" int at_csr_destroy(at_csr_t* c) {
+    if (c == nullptr) return AT_OK;
+    cudaFree(c->d_indptr);
+    cudaFree(c->d_indices);
+    cudaFree(c->d_data);
+    delete c;
+    return AT_OK;
+}
+
+extern "C" int at_csr_info(const at_csr_t* c, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                           int* uniform_nnz, int* data_dtype) {
+    AT_REQUIRE(c != nullptr, "at_csr_info: null handle");
+    if (n_rows) *n_rows = c->n_rows;
+    if (n_cols) *n_cols = c->n_cols;
+    if (nnz) *nnz = c->nnz;
+    if (uniform_nnz) *uniform_nnz = c->uniform_nnz;
+    if (data_dtype) *data_dtype = c->data_dtype;
+    return AT_OK;
+}
+
+static int decode_variant(int variant, int& vpl, int& rows_per_warp, bool& bulk, bool& general) {
+    // bits 0-2: float4 per lane per nonzero (1, 2, 4); bits 4-7: rows per warp;
+    // bit 8: bulk-copy (TMA) staging off; bit 9: force the general-CSR kernel.
+    vpl = variant & 7;
+    rows_per_warp = (variant >> 4) & 15;
+    bulk = ((variant >> 8) & 1) == 0;
+    general = ((variant >> 9) & 1) != 0;
+    if (vpl == 0) vpl = 2;
+    if (rows_per_warp == 0) rows_per_warp = 4;
+    if (vpl != 1 && vpl != 2 && vpl != 4)
+        return set_error(AT_ERR_INVALID, "at_spmm: variant selects %d float4 per lane", vpl);
+    if (rows_per_warp * kWarps > kMaxRowsPerCta)
+        return set_error(AT_ERR_INVALID, "at_spmm: variant selects %d rows per warp", rows_per_warp);
+    return AT_OK;
+}
+
+extern "C" int at_spmm(const at_csr_t* csr, const void* X, int x_dtype, int64_t ldx, void* Y,
+                       int y_dtype, int64_t ldy, int64_t n_fields, int spmm_variant,
+                       void* stream) {
+    AT_REQUIRE(csr != nullptr && X != nullptr && Y != nullptr, "at_spmm: null argument");
+    AT_REQUIRE(n_fields >= 0 && ldx >= n_fields && ldy >= n_fields,
+               "at_spmm: leading dimensions (%lld, %lld) smaller than n_fields %lld",
+               (long long)ldx, (long long)ldy, (long long)n_fields);
+    const int want_y = (csr->data_dtype == AT_F64 || x_dtype == AT_F64) ? AT_F64 : AT_F32;
+    AT_REQUIRE(y_dtype == want_y, "at_spmm: result dtype must be %s (numpy result_type)",
+               want_y == AT_F64 ? "float64" : "float32");
+    if (n_fields == 0 || csr->n_rows == 0) return AT_OK;
+    cudaStream_t st = as_stream(stream);
+
+    if (csr->data_dtype == AT_F32 && x_dtype == AT_F32) {
+        AT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "at_spmm: ldx, ldy must be multiples of 4");
+        AT_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
+                   "at_spmm: X and Y must be 16-byte aligned");
+        int vpl, rpw;
+        bool bulk, general;
+        int rc = decode_variant(spmm_variant, vpl, rpw, bulk, general);
+        if (rc != AT_OK) return rc;
+        SpmmArgs a;
+        a.indptr = csr->d_indptr;
+        a.indices = csr->d_indices;
+        a.data = static_cast<const float*>(csr->d_data);
+        a.X = static_cast<const float4*>(X);
+        a.Y = static_cast<float4*>(Y);
+        a.ldx4 = static_cast<size_t>(ldx / 4);
+        a.ldy4 = static_cast<size_t>(ldy / 4);
+        a.n_rows = static_cast<int>(csr->n_rows);
+        // Columns beyond n_fields up to the next multiple of 4 are padding inside ld.
+        a.n_vec = static_cast<int>((n_fields + 3) / 4);
+        a.rows_per_cta = rpw * kWarps;
+        switch (vpl) {
+            case 1: return launch_f32<1>(csr, a, bulk, general, st);
+            case 2: return launch_f32<2>(csr, a, bulk, general, st);
+            default: return launch_f32<4>(csr, a, bulk, general, st);
+        }
+    }
+    if (csr->data_dtype == AT_F64 && x_dtype == AT_F32)
+        return launch_generic<double, float, double>(csr, X, ldx, Y, ldy, n_fields, st);
+    if (csr->data_dtype == AT_F64 && x_dtype == AT_F64)
+        return launch_generic<double, double, double>(csr, X, ldx, Y, ldy, n_fields, st);
+    if (csr->data_dtype == AT_F32 && x_dtype == AT_F64)
+        return launch_generic<float, double, double>(csr, X, ldx, Y, ldy, n_fields, st);
+    return set_error(AT_ERR_INVALID, "at_spmm: bad dtype codes");
+}
+
+// ---- epilogue handle --------------------------------------------------------------------
+extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_segments,
+                                  const at_epi_col_t* cols, int32_t n_out_cols,
+                                  at_epilogue_t** out) {
+    AT_REQUIRE(out != nullptr, "at_epilogue_create: out is null");
+    *out = nullptr;
+    AT_REQUIRE(segments != nullptr && n_segments > 0 && cols != nullptr && n_out_cols > 0,
+               "at_epilogue_create: empty program");
+    std::vector<EpiTile> tiles;
+    int n_in_cols = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        const at_epi_segment_t& g = segments[s];
+        AT_REQUIRE(g.kind >= AT_EPI_PLAIN && g.kind <= AT_EPI_RT2RTQ,
+                   "at_epilogue_create: segment %d has unknown kind %d", s, g.kind);
+        AT_REQUIRE(g.in_col >= 0 && g.in_col % 4 == 0 && g.n_in > 0 && g.n_in % 4 == 0,
+                   "at_epilogue_create: segment %d: in_col and n_in must be multiples of 4", s);
+        int out_per_vec = 4;
+        if (g.kind == AT_EPI_QT2R || g.kind == AT_EPI_RT2Q) out_per_vec = 2;
+        if (g.kind == AT_EPI_QT2QTR || g.kind == AT_EPI_RT2RTQ) out_per_vec = 6;
+        const int align = g.kind == AT_EPI_PLAIN || g.kind == AT_EPI_UV2DDFF || g.kind == AT_EPI_DDFF2UV ? 4 : 2;
+        AT_REQUIRE(g.out_col >= 0 && g.out_col % align == 0,
+                   "at_epilogue_create: segment %d: out_col must be a multiple of %d", s, align);
+        const int n_vec = g.n_in / 4;
+        AT_REQUIRE(g.out_col + n_vec * out_per_vec <= n_out_cols,
+                   "at_epilogue_create: segment %d writes past n_out_cols", s);
+        for (int v0 = 0; v0 < n_vec; v0 += kWarp) {
+            EpiTile t;
+            t.kind = g.kind;
+            t.in_vec0 = g.in_col / 4 + v0;
+            t.n_vec = std::min(kWarp, n_vec - v0);
+            t.out_col0 = g.out_col + v0 * out_per_vec;
+            tiles.push_back(t);
+        }
+        n_in_cols = std::max(n_in_cols, g.in_col + g.n_in);
+    }
+    AT_REQUIRE(tiles.size() <= 65535, "at_epilogue_create: too many column tiles");
+    std::vector<ColF32> h32(static_cast<size_t>(n_out_cols));
+    std::vector<ColF64> h64(static_cast<size_t>(n_out_cols));
+    for (int c = 0; c < n_out_cols; ++c) {
+        h32[static_cast<size_t>(c)] = {static_cast<float>(cols[c].lo), static_cast<float>(cols[c].hi),
+                                       static_cast<float>(cols[c].pressure), cols[c].flags};
+        h64[static_cast<size_t>(c)] = {cols[c].lo, cols[c].hi, cols[c].pressure, cols[c].flags};
+    }
+    at_epilogue* e = new at_epilogue();
+    e->n_tiles = static_cast<int32_t>(tiles.size());
+    e->n_in_cols = n_in_cols;
+    e->n_out_cols = n_out_cols;
+    cudaGetDevice(&e->device);
+    cudaError_t ce;
+    if ((ce = cudaMalloc(&e->d_tiles, tiles.size() * sizeof(EpiTile))) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_cols32, h32.size() * sizeof(ColF32))) != cudaSuccess ||
+        (ce = cudaMalloc(&e->d_cols64, h64.size() * sizeof(ColF64))) != cudaSuccess ||
+        (ce = cudaMemcpy(e->d_tiles, tiles.data(), tiles.size() * sizeof(EpiTile), cudaMemcpyHostToDevice)) !=
+            cudaSuccess ||
+        (ce = cudaMemcpy(e->d_cols32, h32.data(), h32.size() * sizeof(ColF32), cudaMemcpyHostToDevice)) !=
+            cudaSuccess ||
+        (ce = cudaMemcpy(e->d_cols64, h64.data(), h64.size() * sizeof(ColF64), cudaMemcpyHostToDevice)) !=
+            cudaSuccess) {
+        at_epilogue_destroy(e);
+        return set_error(AT_ERR_CUDA, "at_epilogue_create: %s", cudaGetErrorString(ce));
+    }
+    *out = e;
+    return AT_OK;
+}
+
+extern "C" int at_epilogue_destroy(at_epilogue_t* e) {
+    if (e == nullptr) return AT_OK;
+    cudaFree(e->d_tiles);
+    cudaFree(e->d_cols32);
+    cudaFree(e->d_cols64);
+    delete e;
+    return AT_OK;
+}
+
+extern "C" int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi, const float* X,
+                             int64_t ldx, float* Y, int64_t ldy, const uint8_t* row_mask,
+                             void* stream) {
+    AT_REQUIRE(csr != nullptr && epi != nullptr && X != nullptr && Y != nullptr,
+               "at_spmm_fused: null argument");
+    AT_REQUIRE(csr->data_dtype == AT_F32, "at_spmm_fused: float32 matrices only");
+    AT_REQUIRE(ldx % 4 == 0 && ldx >= epi->n_in_cols, "at_spmm_fused: ldx %lld too small or not a multiple of 4",
+               (long long)ldx);
+    AT_REQUIRE(ldy % 2 == 0 && ldy >= epi->n_out_cols, "at_spmm_fused: ldy %lld too small or odd", (long long)ldy);
+    AT_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
+               "at_spmm_fused: X and Y must be 16-byte aligned");
+    AT_REQUIRE(ldy % 4 == 0, "at_spmm_fused: ldy must be a multiple of 4");
+    if (csr->n_rows == 0) return AT_OK;
+    FusedArgs f;
+    f.s.indptr = csr->d_indptr;
+    f.s.indices = csr->d_indices;
+    f.s.data = static_cast<const float*>(csr->d_data);
+    f.s.X = reinterpret_cast<const float4*>(X);
+    f.s.Y = nullptr;
+    f.s.ldx4 = static_cast<size_t>(ldx / 4);
+    f.s.ldy4 = 0;
+    f.s.n_rows = static_cast<int>(csr->n_rows);
+    f.s.n_vec = 0;
+    f.s.rows_per_cta = 4 * kWarps;
+    f.tiles = epi->d_tiles;
+    f.cols = epi->d_cols32;
+    f.row_mask = row_mask;
+    f.Yf = Y;
+    f.ldy = static_cast<size_t>(ldy);
+    dim3 grid(static_cast<unsigned>((csr->n_rows + f.s.rows_per_cta - 1) / f.s.rows_per_cta),
+              static_cast<unsigned>(epi->n_tiles));
+    spmm_fused_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(f);
+    AT_LAUNCH_CHECK("spmm_fused_kernel");
+    return AT_OK;
+}
+
+template <typename T>
+static int launch_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void* X, int64_t ldx, void* Y,
+                            int64_t ldy, const typename ColStore<T>::type* cols, const uint8_t* row_mask,
+                            cudaStream_t st) {
+    PointwiseArgs<T> f;
+    f.tiles = epi->d_tiles;
+    f.cols = cols;
+    f.row_mask = row_mask;
+    f.X = static_cast<const T*>(X);
+    f.Y = static_cast<T*>(Y);
+    f.ldx = static_cast<size_t>(ldx);
+    f.ldy = static_cast<size_t>(ldy);
+    f.n_rows = n_rows;
+    f.rows_per_cta = 4 * kWarps;
+    const int64_t gx = (n_rows + f.rows_per_cta - 1) / f.rows_per_cta;
+    if (gx >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_pointwise: too many rows");
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(epi->n_tiles));
+    pointwise_kernel<T><<<grid, kThreads, 0, st>>>(f);
+    AT_LAUNCH_CHECK("pointwise_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void* X, int64_t ldx, void* Y,
+                            int64_t ldy, int dtype, const uint8_t* row_mask, void* stream) {
+    AT_REQUIRE(epi != nullptr && X != nullptr && Y != nullptr, "at_pointwise: null argument");
+    AT_REQUIRE(n_rows >= 0, "at_pointwise: negative n_rows");
+    AT_REQUIRE(dtype == AT_F32 || dtype == AT_F64, "at_pointwise: bad dtype code");
+    AT_REQUIRE(ldx % 4 == 0 && ldx >= epi->n_in_cols, "at_pointwise: ldx %lld too small or not a multiple of 4",
+               (long long)ldx);
+    AT_REQUIRE(ldy % 4 == 0 && ldy >= epi->n_out_cols, "at_pointwise: ldy %lld too small or not a multiple of 4",
+               (long long)ldy);
+    AT_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
+               "at_pointwise: X and Y must be 16-byte aligned");
+    if (n_rows == 0) return AT_OK;
+    if (dtype == AT_F32)
+        return launch_pointwise<float>(epi, n_rows, X, ldx, Y, ldy, epi->d_cols32, row_mask, as_stream(stream));
+    return launch_pointwise<double>(epi, n_rows, X, ldx, Y, ldy, epi->d_cols64, row_mask, as_stream(stream));
+}

@@ -1,0 +1,259 @@
+/*
+ * at_b200.h — C-ABI of libat_b200.so: the B200 (sm_100a) field-transform hot path.
+ *
+ * This is the drop-in boundary of the regrid / spatial / pointwise path of
+ * ecmwf/anemoi-transform (reference v0.4.2).  The reference is pure Python; its native
+ * arithmetic lives in scipy.sparse (csr_matvec), scipy.spatial (cKDTree) and numpy ufuncs.
+ * Every entry point below names the reference call site (file:line under
+ * src/anemoi/transform/) whose native work it replaces.  The Python host side
+ * (anemoi_transform_b200/_cabi.py) binds these with ctypes; see INTEGRATION.md for the
+ * stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status (AT_OK == 0); at_last_error() gives the message
+ *     of the last failure on the calling thread;
+ *   - "host" / "device" in a parameter comment says where the pointer must live;
+ *   - device buffers are caller-owned (torch tensors on the Python side); the library
+ *     allocates device memory only inside opaque handles (at_csr_t, at_epilogue_t,
+ *     at_knn_t, at_pipeline_t), released by the matching *_destroy;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no torch / numpy types appear in any signature.
+ */
+#ifndef AT_B200_H
+#define AT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define AT_API __attribute__((visibility("default")))
+#else
+#define AT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------------------------------------------------------- status / dtypes --- */
+#define AT_OK 0
+#define AT_ERR_INVALID 1     /* bad argument (shape, alignment, dtype, null pointer)   */
+#define AT_ERR_CUDA 2        /* a CUDA runtime call or a kernel launch failed          */
+#define AT_ERR_NOMEM 3       /* device / host allocation failed                        */
+#define AT_ERR_UNSUPPORTED 4 /* valid request outside what the kernels implement       */
+#define AT_ERR_INDEX 5       /* an index was out of range (numpy would raise IndexError) */
+
+#define AT_F32 0
+#define AT_F64 1
+#define AT_I32 0
+#define AT_I64 1
+
+typedef struct at_csr at_csr_t;
+typedef struct at_epilogue at_epilogue_t;
+typedef struct at_knn at_knn_t;
+typedef struct at_pipeline at_pipeline_t;
+
+AT_API const char* at_last_error(void);
+AT_API int at_version(void);
+/* Number of CUDA devices visible; fails (AT_ERR_CUDA) when there is no usable GPU. */
+AT_API int at_device_count(int* count);
+AT_API int at_set_device(int device);
+/* Pin / unpin an existing host allocation so the async copies of at_pipeline_* overlap. */
+AT_API int at_host_register(void* ptr, size_t bytes);
+AT_API int at_host_unregister(void* ptr);
+
+/* ------------------------------------------------------------------ CSR matrix ------ */
+/*
+ * Stage a CSR interpolation matrix once in HBM.
+ * Replaces: MIRMatrix.__init__  filters/fields/regrid.py:281-285
+ *           (np.load(npz) -> scipy.sparse.csr_array((data, indices, indptr), shape)).
+ * indptr/indices/data are HOST pointers in the dtypes the .npz stores
+ * (make-regrid-file.py:150-160); indices are range-checked here.
+ * nnz must be < 2^31 and n_cols < 2^31 (device copies are int32).
+ */
+AT_API int at_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz,
+                  const void* indptr, int indptr_dtype,   /* host, AT_I32 | AT_I64, n_rows+1 */
+                  const void* indices, int indices_dtype, /* host, AT_I32 | AT_I64, nnz      */
+                  const void* data, int data_dtype,       /* host, AT_F32 | AT_F64, nnz      */
+                  at_csr_t** out);
+AT_API int at_csr_destroy(at_csr_t* csr);
+/* uniform_nnz = k when every row has exactly k stored entries, else 0. */
+AT_API int at_csr_info(const at_csr_t* csr, int64_t* n_rows, int64_t* n_cols, int64_t* nnz,
+                int* uniform_nnz, int* data_dtype);
+
+/*
+ * Y[n_rows, n_fields] = A · X[n_cols, n_fields]   (point-major, row-major, ld in elements).
+ * Replaces: MIRMatrix.__call__ `self.matrix @ data`  filters/fields/regrid.py:309-310
+ *           (scipy.sparse._sparsetools csr_matvec), batched over fields.
+ * Semantics are scipy's, bit for bit: per (row, field) the products are accumulated
+ * sequentially in storage order, starting from +0, with separate multiply and add (no FMA);
+ * explicit zeros are not skipped (0·NaN = NaN); an empty row gives 0.
+ * Result dtype follows numpy: y_dtype must be F64 if the matrix or X is F64, else F32.
+ * The f32·f32 fast path needs ldx, ldy multiples of 4 and 16-byte aligned X, Y.
+ * spmm_variant: 0 = default tuning; other values select kernel shapes.
+ */
+AT_API int at_spmm(const at_csr_t* csr,
+            const void* X, int x_dtype, int64_t ldx, /* device */
+            void* Y, int y_dtype, int64_t ldy,       /* device */
+            int64_t n_fields, int spmm_variant, void* stream);
+
+/* ------------------------------------------------------------ fused epilogue -------- */
+/*
+ * A pointwise program over the columns of a point-major batch, fused into the SpMM
+ * epilogue (at_spmm_fused) or run on its own (at_pointwise).  Columns are described in
+ * segments; within a segment the kind is uniform and partner columns are adjacent.
+ *
+ *   AT_EPI_PLAIN     in (a)        -> out (a)             clip / mask only
+ *   AT_EPI_UV2DDFF   in (u, v)     -> out (ws, wdir)      uv_to_ddff.py:77-101
+ *   AT_EPI_DDFF2UV   in (ws, wdir) -> out (u, v)          uv_to_ddff.py:103-127
+ *   AT_EPI_QT2R      in (q, t)     -> out (r)             q_to_r.py:69-73
+ *   AT_EPI_QT2QTR    in (q, t)     -> out (q, t, r)       q_to_r.py:69-73, return_inputs="all"
+ *   AT_EPI_RT2Q      in (r, t)     -> out (q)             q_to_r.py:75-81
+ *   AT_EPI_RT2RTQ    in (r, t)     -> out (r, t, q)       q_to_r.py:75-81, return_inputs="all"
+ *
+ * After the kind's conversion every OUTPUT column c applies, in this order,
+ *   clip:  np.clip(x, lo, hi) with NaN passing through     clipper.py:67-70
+ *   mask:  x = NaN where row_mask[row] != 0                 apply_mask.py:184-185
+ * as selected by cols[c].flags.
+ */
+#define AT_EPI_PLAIN 0
+#define AT_EPI_UV2DDFF 1
+#define AT_EPI_DDFF2UV 2
+#define AT_EPI_QT2R 3
+#define AT_EPI_QT2QTR 4
+#define AT_EPI_RT2Q 5
+#define AT_EPI_RT2RTQ 6
+
+#define AT_COL_CLIP_LO 1u /* lo is set  */
+#define AT_COL_CLIP_HI 2u /* hi is set  */
+#define AT_COL_MASK 4u    /* apply row_mask to this column */
+
+typedef struct {
+    int32_t kind;    /* AT_EPI_*                                                        */
+    int32_t in_col;  /* first input column; multiple of 4                               */
+    int32_t n_in;    /* input columns in the segment (even for pair kinds)              */
+    int32_t out_col; /* first output column; multiple of 2 (of 4 for PLAIN)             */
+} at_epi_segment_t;
+
+typedef struct {
+    double lo, hi;    /* clip bounds (used when the flag is set); rounded to float32 on
+                         the float32 path, as numpy rounds Python scalars (NEP 50)      */
+    double pressure;  /* Pa; read on the humidity OUTPUT column of QT / RT kinds        */
+    uint32_t flags;   /* AT_COL_*                                                       */
+    uint32_t reserved;
+} at_epi_col_t;
+
+/* segments / cols are HOST arrays; cols has n_out_cols entries indexed by output column. */
+AT_API int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_segments,
+                       const at_epi_col_t* cols, int32_t n_out_cols, at_epilogue_t** out);
+AT_API int at_epilogue_destroy(at_epilogue_t* epi);
+
+/* Y = epilogue(A · X).  f32 only.  row_mask: device uint8[n_rows] or NULL. */
+AT_API int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi,
+                  const float* X, int64_t ldx, float* Y, int64_t ldy,
+                  const uint8_t* row_mask, void* stream);
+/* Y = epilogue(X) on a resident batch of n_rows points (the standalone pointwise filters).
+ * dtype AT_F32 | AT_F64 is the type of X and Y (numpy keeps the dtype of the field). */
+AT_API int at_pointwise(const at_epilogue_t* epi, int64_t n_rows,
+                 const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype,
+                 const uint8_t* row_mask, void* stream);
+
+/* --------------------------------------------------------------- layout ------------- */
+/*
+ * dst[c, r] = src[r, c]: field-major [n_fields, n_points] <-> point-major
+ * [n_points, n_fields] (the FieldList delivers one array per field: regrid.py:309).
+ * elem_size 4 or 8.  ld in elements.
+ */
+AT_API int at_transpose(const void* src, int64_t rows, int64_t cols, int64_t ld_src,
+                 void* dst, int64_t ld_dst, int elem_size, void* stream);
+/*
+ * Y[i, :] = X[idx[i], :]  for i < n_out — the nearest-neighbour / masked regrid gather.
+ * Replaces: `data[..., self.nearest_grid_points]` regrid.py:380 and
+ *           `data[..., self.mask]` regrid.py:420 (numpy fancy indexing).
+ * idx: device int64[n_out]; an index outside [0, n_src) sets *err_flag (device int32,
+ * may be NULL) to 1 and writes nothing for that row (numpy raises IndexError).
+ */
+AT_API int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src,
+                   const void* X, int64_t ldx, void* Y, int64_t ldy,
+                   int64_t n_fields, int elem_size, int32_t* err_flag, void* stream);
+/* mask[i] = OP(values[i], threshold) — MaskVariable._compute_mask apply_mask.py:160-163.
+ * op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.  values: device f32 with element stride `stride`. */
+AT_API int at_compare_mask(const float* values, int64_t stride, int64_t n, int op, float threshold,
+                    uint8_t* mask, void* stream);
+
+/* ------------------------------------------------ end-to-end host pipeline ----------- */
+/*
+ * Regrid host-resident fields through the GPU: chunked H2D -> pack -> SpMM -> unpack ->
+ * D2H on three streams with double buffering.  This is the call a FieldList-in /
+ * FieldList-out RegridFilter.forward makes (regrid.py:174-208), batched.
+ * fields_in[f] : host float32[n_cols], fields_out[f] : host float32[n_rows]
+ * (pinned memory lets the copies overlap; pageable memory still works).
+ */
+AT_API int at_pipeline_create(const at_csr_t* csr, int32_t chunk_fields, at_pipeline_t** out);
+AT_API int at_pipeline_destroy(at_pipeline_t* p);
+AT_API int at_pipeline_regrid(at_pipeline_t* p, const float* const* fields_in,
+                       float* const* fields_out, int64_t n_fields);
+
+/* --------------------------------------------------------------- kNN / masks -------- */
+/*
+ * Build the bucketed search structure over source points (float64 xyz, SoA).
+ * Replaces: scipy.spatial.cKDTree(points) construction
+ *           spatial.py:96, 396, 501, 533, 628-632.
+ * x, y, z: float64[n]; host pointers unless on_device != 0.
+ * cell_size <= 0 picks the cell from the point density.
+ */
+AT_API int at_knn_create(const double* x, const double* y, const double* z, int64_t n,
+                  int on_device, double cell_size, at_knn_t** out);
+AT_API int at_knn_destroy(at_knn_t* knn);
+/*
+ * k nearest sources of each query, ascending by (d², index).
+ * Replaces: cKDTree.query(points, k[, distance_upper_bound])  spatial.py:96,396,501,628-632.
+ * d² = ((dx·dx)+(dy·dy))+(dz·dz) in float64, unfused (bitwise cKDTree's p=2 distance);
+ * dist_out = sqrt(d²).  Candidates need d² < upper_bound² (strict; upper_bound = +inf for
+ * none); unfilled slots get index n and distance +inf, as cKDTree pads.
+ * idx_out int64[nq,k]; dist_out float64[nq,k] or NULL;
+ * tie_out uint8[nq] or NULL: bit0 = two selected neighbours have equal d²,
+ *                            bit1 = the k-th and the (k+1)-th candidates have equal d²
+ * (the only queries on which cKDTree's traversal order may legitimately pick differently).
+ * All pointers device.  k <= 32.
+ */
+AT_API int at_knn_query(const at_knn_t* knn, const double* qx, const double* qy, const double* qz,
+                 int64_t nq, int k, double upper_bound,
+                 int64_t* idx_out, double* dist_out, uint8_t* tie_out, void* stream);
+/*
+ * mark[j] = 1 for every source j with d²(q, j) <= r·r for some query q (mark is OR-ed into;
+ * zero it first).  Replaces: cKDTree.query_ball_point + Python set-union  spatial.py:533-534.
+ */
+AT_API int at_ball_mark(const at_knn_t* knn, const double* qx, const double* qy, const double* qz,
+                 int64_t nq, double r, uint8_t* mark, void* stream);
+/* out_host = min over sources of the distance to their 2nd nearest source (self included
+ * as the 1st) — `_resolution`  spatial.py:93-97.  Synchronises the stream. */
+AT_API int at_min_nn_distance(const at_knn_t* knn, double* out_host, void* stream);
+/* Sorted indices of the non-zero bytes of mark[n] (stream compaction):
+ * `np.array(sorted(set(...)))` spatial.py:534 / boolean-mask selection.
+ * out_idx: device int64[n] (capacity n); *count_host receives the count. Synchronises. */
+AT_API int at_compact_mask(const uint8_t* mark, int64_t n, int64_t* out_idx, int64_t* count_host,
+                    void* stream);
+/* cropping_mask  spatial.py:236-275 — inclusive box with ±360 longitude wrap. */
+AT_API int at_cropping_mask(const double* lats, const double* lons, int64_t n,
+                     double north, double west, double south, double east,
+                     uint8_t* mask, void* stream);
+/*
+ * Per cropped global point: inside | close | too_far  — the body of the Python loop of
+ * cutout_mask spatial.py:404-424 with Triangle3D.intersect spatial.py:189-233.
+ * lam xyz: float64[n_lam] SoA; global xyz: float64[nq] SoA; nbr_idx int64[nq,k] and
+ * nbr_dist float64[nq,k] from at_knn_query (ascending).  max_distance < 0 means None.
+ * dot_mode: 0 = unfused dot products, 1 = FMA-chain dot products (OpenBLAS ddot as numpy
+ * calls it on x86-64 with FMA; np.cross is always unfused).
+ * out uint8[nq].  All pointers device.
+ */
+AT_API int at_cutout_classify(const double* lx, const double* ly, const double* lz, int64_t n_lam,
+                       const double* gx, const double* gy, const double* gz, int64_t nq,
+                       const int64_t* nbr_idx, const double* nbr_dist, int k,
+                       double min_distance, double max_distance, int dot_mode,
+                       uint8_t* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AT_B200_H */
