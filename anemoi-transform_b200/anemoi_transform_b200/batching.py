@@ -1,0 +1,46 @@
+"""Moving FieldList values in and out of point-major device batches."""
+
+from __future__ import annotations
+
+from typing import Any, Sequence
+
+import numpy as np
+
+from .device import DeviceBatch, require_cuda, round_up
+from .fields import device_column_of
+
+
+def fields_to_batch(fields: Sequence[Any]) -> DeviceBatch:
+    """A point-major batch whose column j holds the values of fields[j].
+
+    Fields already resident in HBM (outputs of an earlier filter of this package) are not
+    round-tripped through the host: consecutive columns of one batch are used in place,
+    other arrangements are re-packed on the device.
+    """
+    torch = require_cuda()
+    cols = [device_column_of(f) for f in fields]
+    if cols and all(c is not None for c in cols):
+        batches = {id(c[0]) for c in cols}
+        first_batch, c0 = cols[0]
+        n = len(cols)
+        consecutive = len(batches) == 1 and all(c[1] == c0 + j for j, c in enumerate(cols))
+        align = 4 if first_batch.data.element_size() == 4 else 2
+        if consecutive and c0 % align == 0 and c0 + round_up(n, 4) <= first_batch.data.shape[1]:
+            return DeviceBatch(first_batch.data[:, c0 : c0 + round_up(n, 4)], n)
+        dtypes = {c[0].data.dtype for c in cols}
+        if len(dtypes) == 1 and len({c[0].n_points for c in cols}) == 1:
+            ld = round_up(n, 4)
+            out = torch.zeros((first_batch.n_points, ld), dtype=first_batch.data.dtype, device=first_batch.data.device)
+            if len(batches) == 1:
+                index = torch.tensor([c[1] for c in cols], device=out.device, dtype=torch.int64)
+                out[:, :n] = first_batch.data.index_select(1, index)
+            else:
+                for j, (b, c) in enumerate(cols):
+                    out[:, j] = b.data[:, c]
+            return DeviceBatch(out, n)
+    return DeviceBatch.from_host_fields([f.to_numpy(flatten=True) for f in fields])
+
+
+def numpy_dtype_of(batch: DeviceBatch):
+    torch = require_cuda()
+    return np.float32 if batch.data.dtype == torch.float32 else np.float64

@@ -312,11 +312,14 @@ def gather_rows(X, idx, n_fields: int | None = None, out=None):
 
 
 def compare_mask(values, op: int, threshold: float):
-    """uint8 mask = OP(values, threshold) for a 1-D (possibly strided) float32 CUDA tensor."""
+    """uint8 mask = OP(values, threshold) for a 1-D (possibly strided) float CUDA tensor."""
     torch = _torch()
+    if values.dtype not in (torch.float32, torch.float64):
+        values = values.to(torch.float64)
     n = int(values.shape[0])
     mask = torch.empty((n,), dtype=torch.uint8, device=values.device)
-    call("at_compare_mask", _ptr(values), values.stride(0) if n > 1 else 1, n, int(op), float(threshold), _ptr(mask), stream_ptr())
+    code = AT_F32 if values.dtype == torch.float32 else AT_F64
+    call("at_compare_mask", _ptr(values), code, values.stride(0) if n > 1 else 1, n, int(op), float(threshold), _ptr(mask), stream_ptr())
     return mask
 
 
@@ -326,6 +329,7 @@ class DeviceBatch:
     def __init__(self, data, n_fields: int):
         self.data = data
         self.n_fields = int(n_fields)
+        self._host = None  # lazily unpacked field-major copy, shared by the batch's fields
 
     @property
     def n_points(self) -> int:
@@ -355,11 +359,16 @@ class DeviceBatch:
         return cls(pm, n_fields)
 
     def to_host_fields(self) -> np.ndarray:
-        """→ numpy [n_fields, n_points] (field-major)."""
-        torch = _torch()
-        fm = torch.empty((self.n_fields, self.n_points), dtype=self.data.dtype, device=self.data.device)
-        call("at_transpose", _ptr(self.data), self.n_points, self.n_fields, self.data.stride(0), _ptr(fm), fm.stride(0), self.data.element_size(), stream_ptr())
-        return fm.cpu().numpy()
+        """→ numpy [n_fields, n_points] (field-major); unpacked and downloaded once."""
+        if self._host is None:
+            torch = _torch()
+            fm = torch.empty((self.n_fields, self.n_points), dtype=self.data.dtype, device=self.data.device)
+            call("at_transpose", _ptr(self.data), self.n_points, self.n_fields, self.data.stride(0), _ptr(fm), fm.stride(0), self.data.element_size(), stream_ptr())
+            self._host = fm.cpu().numpy()
+        return self._host
+
+    def host_column(self, col: int) -> np.ndarray:
+        return self.to_host_fields()[col]
 
 
 class HostPipeline:

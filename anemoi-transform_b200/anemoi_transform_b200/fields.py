@@ -92,12 +92,11 @@ class NewDataField(WrappedField):
 class DeviceColumnField(WrappedField):
     """Template metadata, values = column `col` of a point-major `DeviceBatch` in HBM."""
 
-    def __init__(self, field: Any, batch: Any, col: int) -> None:
+    def __init__(self, field: Any, batch: Any, col: int, shape: tuple[int, ...] | None = None) -> None:
         super().__init__(field)
         self._batch = batch
         self._col = int(col)
-        self.shape = (batch.n_points,)
-        self._host: np.ndarray | None = None
+        self.shape = tuple(shape) if shape is not None else (batch.n_points,)
 
     @property
     def batch(self) -> Any:
@@ -112,11 +111,12 @@ class DeviceColumnField(WrappedField):
         return self.to_numpy(flatten=True)
 
     def to_numpy(self, flatten: bool = False, dtype: type | None = None, index: Any | None = None) -> np.ndarray:
-        if self._host is None:
-            self._host = self._batch.data[:, self._col].contiguous().cpu().numpy()
-        data = self._host.copy()  # each call hands out a fresh array, like NewDataField.flatten()
+        # each call hands out a fresh array (reference NewDataField.to_numpy(flatten=True) copies)
+        data = self._batch.host_column(self._col).copy()
         if dtype is not None:
             data = data.astype(dtype)
+        if not flatten:
+            data = data.reshape(self.shape)
         if index is not None:
             data = data[index]
         return data
@@ -276,8 +276,8 @@ def new_field_from_numpy(array: np.ndarray, *, template: Any, **metadata: Any) -
     return NewMetadataField(NewDataField(template, array), **metadata)
 
 
-def new_field_from_device_column(batch: Any, col: int, *, template: Any, **metadata: Any) -> NewMetadataField:
-    return NewMetadataField(DeviceColumnField(template, batch, col), **metadata)
+def new_field_from_device_column(batch: Any, col: int, *, template: Any, shape=None, **metadata: Any) -> NewMetadataField:
+    return NewMetadataField(DeviceColumnField(template, batch, col, shape), **metadata)
 
 
 def new_field_with_metadata(template: Any, **metadata: Any) -> NewMetadataField:

@@ -1,0 +1,54 @@
+"""Top-level filter registry — reference `filters/__init__.py:13-64`.
+
+The field-filter registry is merged into the top-level one with duplicate detection
+(`_merge_registries`, reference 22-33); the dispatchers `clip` / `mask` register directly at
+the top level.  Tabular (pandas) filters are outside the hot path and not provided; the
+dispatchers raise a clear error if asked for a tabular configuration.
+"""
+
+from __future__ import annotations
+
+from typing import Any
+
+from ..registry import Registry
+from .fields import filter_registry as fields_filter_registry
+
+filter_registry = Registry(__name__, entry_point_group="anemoi.transform.filters")
+
+# importing the modules runs their registration decorators
+from .fields import apply_mask as _apply_mask  # noqa: E402,F401
+from .fields import clipper as _clipper  # noqa: E402,F401
+from .fields import q_to_r as _q_to_r  # noqa: E402,F401
+from .fields import regrid as _regrid  # noqa: E402,F401
+from .fields import uv_to_ddff as _uv_to_ddff  # noqa: E402,F401
+
+
+def _merge_registries() -> None:
+    for source in (fields_filter_registry,):
+        for name, factory in source.factories.items():
+            try:
+                filter_registry.register(name, factory, aliases=source.aliases().get(name, None))
+            except AssertionError as e:
+                raise AssertionError(f"Duplicate filter name: {name} in {source.package} registry") from e
+
+
+def create_filter_by_name(name: str, *, context: Any = None, **config: Any):
+    """Create a filter from its registered name and keyword configuration."""
+    f = filter_registry.create(name, **config)
+    f.context = context
+    return f
+
+
+def create_filter(context: Any, config: Any):
+    """Create a filter from a YAML-style configuration (`"name"` or `{"name": {…}}`)."""
+    f = filter_registry.from_config(config)
+    f.context = context
+    return f
+
+
+_merge_registries()
+
+from . import clip as _clip  # noqa: E402,F401
+from . import mask as _mask  # noqa: E402,F401
+
+__all__ = ["filter_registry", "create_filter", "create_filter_by_name"]

@@ -1,0 +1,258 @@
+"""`regrid` — reference `filters/fields/regrid.py:87-516`.
+
+Same constructor arguments, same interpolator precedence (matrix > mask > method=="nearest"
+> earthkit, `_interpolator` 432-467) and the same output wrapping
+(`NewLatLonField(NewMetadataField(NewDataField…))`, regrid.py:312).  What changes is where
+the arithmetic runs: the per-field Python loop of `_interpolate` (regrid.py:204-208) becomes
+one batched device pass —
+
+    MIRMatrix                     CSR staged once in HBM, `at_spmm` over all fields
+    ScipyKDTreeNearestNeighbours  `spatial.nearest_grid_points` (device kNN) + `at_gather_rows`
+    MaskedRegrid                  `at_gather_rows` with the mask's indices
+
+Host fields are uploaded in chunks and packed point-major; fields already resident in HBM
+(outputs of another filter of this package) are used in place.  Outputs stay resident and
+are downloaded when `to_numpy()` is first called.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Any
+
+import numpy as np
+
+from ... import ekd
+from ...batching import fields_to_batch
+from ...device import CsrMatrix, DeviceBatch, gather_rows, require_cuda
+from ...fields import new_field_from_device_column, new_field_from_latitudes_longitudes, new_fieldlist_from_list
+from ...filter import Filter
+from . import filter_registry
+
+LOG = logging.getLogger(__name__)
+
+
+def as_gridspec(grid: Any) -> dict[str, Any] | None:
+    if grid is None:
+        return None
+    if isinstance(grid, (str, list, tuple)):
+        return {"grid": grid}
+    return grid
+
+
+def as_griddata(grid: Any) -> dict[str, Any] | None:
+    """Grid given as a field, a {latitudes, longitudes} dict or a named grid."""
+    if grid is None:
+        return None
+    if isinstance(grid, ekd.Field) or (hasattr(grid, "grid_points") and hasattr(grid, "to_numpy")):
+        lat, lon = grid.grid_points()
+        return dict(latitudes=lat, longitudes=lon)
+    if isinstance(grid, dict) and "latitudes" in grid and "longitudes" in grid:
+        return grid
+    if isinstance(grid, (str, list, tuple)):
+        from ...grids import lookup
+
+        return lookup(grid)
+    raise ValueError(f"Invalid grid: {grid}")
+
+
+@filter_registry.register("regrid")
+class RegridFilter(Filter):
+    """Regrid fields with a precomputed matrix, a nearest-neighbour search or an index mask."""
+
+    def __init__(
+        self,
+        *,
+        in_grid: Any | None = None,
+        out_grid: Any | None = None,
+        method: str | None = None,
+        matrix: str | None = None,
+        mask: str | None = None,
+        check: bool = False,
+    ) -> None:
+        self.in_grid = in_grid
+        self.out_grid = out_grid
+        self.method = method
+        self.interpolator = make_interpolator(in_grid=in_grid, out_grid=out_grid, method=method, matrix=matrix, mask=mask, check=check)
+
+    def forward(self, data: Any) -> Any:
+        return self._interpolate(data)
+
+    def _interpolate(self, data: Any) -> Any:
+        fields = list(data)
+        if not fields:
+            return new_fieldlist_from_list([])
+        if hasattr(self.interpolator, "regrid_batch"):
+            return new_fieldlist_from_list(self.interpolator.regrid_batch(fields))
+        return new_fieldlist_from_list([self.interpolator(f) for f in fields])
+
+
+class _BatchedInterpolator:
+    """Shared driver: batch the FieldList, transform on the device, wrap the outputs."""
+
+    def __call__(self, field: Any) -> Any:
+        return self.regrid_batch([field])[0]
+
+    def regrid_batch(self, fields: list[Any]) -> list[Any]:
+        self.prepare(fields[0])
+        # numpy dtypes differ per field in principle; batch runs of equal dtype together
+        out: list[Any] = [None] * len(fields)
+        by_dtype: dict[Any, list[int]] = {}
+        for i, f in enumerate(fields):
+            by_dtype.setdefault(_value_dtype(f), []).append(i)
+        for _, idxs in by_dtype.items():
+            batch = fields_to_batch([fields[i] for i in idxs])
+            result = self.apply(batch)
+            lat, lon = self.output_grid(fields[idxs[0]])
+            for j, i in enumerate(idxs):
+                out[i] = new_field_from_latitudes_longitudes(
+                    new_field_from_device_column(result, j, template=fields[i]), latitudes=lat, longitudes=lon
+                )
+        return out
+
+    def prepare(self, first_field: Any) -> None:
+        pass
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        raise NotImplementedError
+
+    def output_grid(self, field: Any):
+        raise NotImplementedError
+
+
+def _value_dtype(field: Any):
+    from ...fields import device_column_of
+
+    col = device_column_of(field)
+    if col is not None:
+        return str(col[0].data.dtype)
+    dt = np.asarray(field.to_numpy(flatten=True)).dtype if not hasattr(field, "_b200_dtype") else field._b200_dtype
+    return "torch.float32" if dt == np.float32 else "torch.float64"
+
+
+class MIRMatrix(_BatchedInterpolator):
+    """Matrix created by ``anemoi-transform make-regrid-file`` (npz schema
+    make-regrid-file.py:150-160), applied as a device SpMM."""
+
+    def __init__(self, *, matrix: str, check: bool) -> None:
+        self.check = check
+        if self.check:
+            LOG.warning("Check is not supported by MIRMatrix")
+        loaded = dict(np.load(matrix))
+        self.matrix = CsrMatrix(loaded["matrix_data"], loaded["matrix_indices"], loaded["matrix_indptr"], tuple(loaded["matrix_shape"]))
+        self.in_grid = dict(latitudes=loaded["in_latitudes"], longitudes=loaded["in_longitudes"])
+        self.out_grid = dict(latitudes=loaded["out_latitudes"], longitudes=loaded["out_longitudes"])
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        if batch.n_points != self.matrix.shape[1]:
+            raise ValueError(f"dimension mismatch: matrix has {self.matrix.shape[1]} columns, field has {batch.n_points} points")
+        return DeviceBatch(self.matrix.apply(batch.data, n_fields=batch.n_fields), batch.n_fields)
+
+    def output_grid(self, field: Any):
+        return self.out_grid["latitudes"], self.out_grid["longitudes"]
+
+
+class ScipyKDTreeNearestNeighbours(_BatchedInterpolator):
+    """Nearest-neighbour regridding for grids earthkit-regrid has no matrix for.
+
+    The class name is the reference's (regrid.py:315); the search itself is the bucketed
+    device kNN of `spatial.nearest_grid_points`, not scipy.
+    """
+
+    nearest_grid_points = None
+
+    def __init__(self, *, in_grid: Any, out_grid: Any, method: str, check: bool = False) -> None:
+        if method != "nearest":
+            raise NotImplementedError(f"ScipyKDTreeNearestNeighbours does not support {method}, only 'nearest'")
+        self.in_grid = as_griddata(in_grid)
+        self.out_grid = as_griddata(out_grid)
+        if self.out_grid is None:
+            raise ValueError("out_grid is required, but not provided")
+        if check:
+            LOG.warning("Check is not supported by ScipyKDTreeNearestNeighbours")
+
+    def prepare(self, first_field: Any) -> None:
+        if self.in_grid is None:
+            self.in_grid = as_griddata(first_field)
+            assert self.in_grid is not None, first_field
+        if self.nearest_grid_points is None:
+            from ...spatial import nearest_grid_points
+
+            self.nearest_grid_points = nearest_grid_points(
+                self.in_grid["latitudes"],
+                self.in_grid["longitudes"],
+                self.out_grid["latitudes"],
+                self.out_grid["longitudes"],
+                _as_device=True,
+            )
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        n_in = (batch.n_points,)
+        assert n_in == np.shape(self.in_grid["latitudes"]), (n_in, np.shape(self.in_grid["latitudes"]))
+        assert n_in == np.shape(self.in_grid["longitudes"]), (n_in, np.shape(self.in_grid["longitudes"]))
+        return DeviceBatch(gather_rows(batch.data, self.nearest_grid_points, n_fields=batch.n_fields), batch.n_fields)
+
+    def output_grid(self, field: Any):
+        return self.out_grid["latitudes"], self.out_grid["longitudes"]
+
+
+class MaskedRegrid(_BatchedInterpolator):
+    """Select points with a precomputed index (or boolean) mask (`make-regrid-file
+    global-on-lam-mask`, make-regrid-file.py:239-240)."""
+
+    out_latitudes = None
+    out_longitudes = None
+
+    def __init__(self, *, mask: str, check: bool) -> None:
+        if check:
+            LOG.warning("Check is not supported by MaskedRegrid")
+        self.mask = np.load(mask)["mask"]
+        self._device_index = None
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        torch = require_cuda()
+        if self._device_index is None:
+            m = self.mask
+            if m.dtype == np.bool_:
+                if m.shape[0] != batch.n_points:
+                    raise IndexError(f"boolean index did not match indexed array along axis 0; size of axis is {batch.n_points} but size of corresponding boolean axis is {m.shape[0]}")
+                m = np.nonzero(m)[0]
+            m = np.asarray(m).astype(np.int64)
+            m = np.where(m < 0, m + batch.n_points, m)  # numpy's negative indexing
+            self._device_index = torch.from_numpy(m).cuda()
+        return DeviceBatch(gather_rows(batch.data, self._device_index, n_fields=batch.n_fields), batch.n_fields)
+
+    def output_grid(self, field: Any):
+        if self.out_latitudes is None or self.out_longitudes is None:
+            in_latitudes, in_longitudes = field.grid_points()
+            self.out_latitudes = in_latitudes[self.mask]
+            self.out_longitudes = in_longitudes[self.mask]
+        return self.out_latitudes, self.out_longitudes
+
+
+class EarthkitRegrid:
+    """earthkit-regrid's pre-generated matrices (regrid.py:211-259): needs the earthkit-regrid
+    package and its matrix inventory; neither ships with this package."""
+
+    def __init__(self, *, in_grid: Any, out_grid: Any, method: str = "linear", check: bool = False) -> None:
+        raise NotImplementedError(
+            "regrid: in_grid/out_grid/method configurations resolve to earthkit-regrid's matrix inventory, "
+            "which is outside this package; pass `matrix=` (make-regrid-file), `mask=` or `method='nearest'`"
+        )
+
+
+def _interpolator(*, method: str | None = None, matrix: str | None = None, mask: str | None = None) -> str:
+    if matrix is not None:
+        return "MIRMatrix"
+    if mask is not None:
+        return "MaskedRegrid"
+    if method == "nearest":
+        return "ScipyKDTreeNearestNeighbours"
+    return "EarthkitRegrid"
+
+
+def make_interpolator(in_grid: Any = None, out_grid: Any = None, method: str | None = None, matrix: str | None = None, mask: str | None = None, check: bool | None = None) -> Any:
+    name = _interpolator(method=method, matrix=matrix, mask=mask)
+    kwargs = {"in_grid": in_grid, "out_grid": out_grid, "method": method, "matrix": matrix, "mask": mask, "check": check}
+    kwargs = {k: v for k, v in kwargs.items() if v is not None}
+    return globals()[name](**kwargs)

@@ -1,0 +1,257 @@
+"""Spherical nearest-neighbour and mask functions — drop-in for `anemoi.transform.spatial`.
+
+Same names, arguments, return types and assertions as the reference `spatial.py`; the
+cKDTree build / query / query_ball_point calls and the per-point Python loop of
+`cutout_mask` run on the GPU through libat_b200.so:
+
+    reference spatial.py                      here
+    --------------------                      ----
+    cKDTree(points)                 96,396…   device.KnnIndex          (at_knn_create)
+    .query(points, k, upper_bound)  96,396…   KnnIndex.query           (at_knn_query)
+    .query_ball_point + set-union   533-534   KnnIndex.ball_mark + compact_mask
+    cutout loop + Triangle3D        404-424   at_cutout_classify
+    cropping_mask                   236-275   at_cropping_mask
+
+`latlon_to_xyz` stays numpy on the host ON PURPOSE: numpy's float64 sin/cos are not
+bit-identical to CUDA's, and nearest-neighbour indices are only bit-exact against cKDTree if
+both searches see the same xyz.  It is O(n) preparation, not the search.
+
+Tie policy: neighbours are ordered by (d², index).  On queries where two sources are at
+exactly the same float64 d², cKDTree's pick depends on its traversal order; this
+implementation returns the lowest index.  `nearest_grid_points(..., _return_ties=True)`
+exposes the per-query tie flags.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Any
+
+import numpy as np
+from numpy.typing import NDArray
+
+from .constants import R_earth_km, radian
+from .device import KnnIndex, call, compact_mask, cropping_mask_device, require_cuda, stream_ptr, to_device_f64, _ptr
+
+LOG = logging.getLogger(__name__)
+
+# np.dot on float64 3-vectors: OpenBLAS ddot accumulates with FMA on x86-64 hosts that have
+# it; 0 switches at_cutout_classify to plain left-to-right products.
+CUTOUT_DOT_MODE = 1
+
+
+def xyz_to_latlon(x: NDArray[Any], y: NDArray[Any], z: NDArray[Any]) -> tuple[NDArray[Any], NDArray[Any]]:
+    """Cartesian coordinates → latitude, longitude in degrees (spatial.py:109-129)."""
+    return (
+        np.rad2deg(np.arcsin(np.minimum(1.0, np.maximum(-1.0, z)))),
+        np.rad2deg(np.arctan2(y, x)),
+    )
+
+
+def latlon_to_xyz(lat: NDArray[Any], lon: NDArray[Any], radius: float = 1.0) -> tuple[NDArray[Any], NDArray[Any], NDArray[Any]]:
+    """Latitude, longitude in degrees → Cartesian coordinates on a sphere (spatial.py:132-167)."""
+    phi = np.deg2rad(lat)
+    lda = np.deg2rad(lon)
+    cos_phi = np.cos(phi)
+    x = cos_phi * np.cos(lda) * radius
+    y = cos_phi * np.sin(lda) * radius
+    z = np.sin(phi) * radius
+    return x, y, z
+
+
+def _check_latlon_arrays(lats, lons, global_lats, global_lons) -> None:
+    assert global_lats.ndim == 1
+    assert global_lons.ndim == 1
+    assert lats.ndim == 1
+    assert lons.ndim == 1
+    assert global_lats.shape == global_lons.shape
+    assert lats.shape == lons.shape
+
+
+def _resolution(points_xyz) -> float:
+    """min over points of the distance to the 2nd nearest point (spatial.py:93-97)."""
+    index = points_xyz if isinstance(points_xyz, KnnIndex) else KnnIndex(points_xyz)
+    return index.min_nn_distance()
+
+
+def _distance_km_to_resolution(function: str, distance_km, lam_points, global_points) -> float:
+    """spatial.py:100-106 — a number of km, or the resolution of "lam" / "global" / None."""
+    if isinstance(distance_km, (int, float)):
+        return distance_km / R_earth_km
+    distance = _resolution({"lam": lam_points, "global": global_points, None: global_points}[distance_km])
+    LOG.info(f"{function} using distance = {distance * R_earth_km} km")
+    return distance
+
+
+def cropping_mask(lats: NDArray[Any], lons: NDArray[Any], north: float, west: float, south: float, east: float) -> NDArray[Any]:
+    """Points inside the box, bounds inclusive, longitudes tested at lon and lon ± 360."""
+    require_cuda()
+    mask = cropping_mask_device(np.asarray(lats, dtype=np.float64), np.asarray(lons, dtype=np.float64), north, west, south, east)
+    return mask.cpu().numpy().astype(bool)
+
+
+def _crop_box(lats, lons, distance):
+    north, south = np.amax(lats), np.amin(lats)
+    east, west = np.amax(lons), np.amin(lons)
+    return (np.min([90.0, north + distance]), west - distance, np.max([-90.0, south - distance]), east + distance)
+
+
+def cutout_mask(
+    lats: NDArray[Any],
+    lons: NDArray[Any],
+    global_lats: NDArray[Any],
+    global_lons: NDArray[Any],
+    cropping_distance: float = 2.0,
+    neighbours: int = 5,
+    min_distance_km: int | float | None = None,
+    max_distance_km: int | float | None = None,
+    plot: str | None = None,
+) -> NDArray[Any]:
+    """Mask of the global points to KEEP around a LAM (True = outside the cutout).
+
+    A global point is dropped when it is inside the LAM (a ray from the Earth's centre
+    through it hits a triangle of its `neighbours` nearest LAM points), closer than
+    `min_distance_km` to it, or farther than `max_distance_km` (spatial.py:294-440).
+    """
+    assert cropping_distance >= 0.0, "cropping_distance must be non-negative"
+    assert min_distance_km is None or min_distance_km >= 0.0, "min_distance_km must be non-negative"
+    assert max_distance_km is None or max_distance_km >= 0.0, "max_distance_km must be non-negative"
+    assert neighbours > 0, "neighbours must be positive"
+    _check_latlon_arrays(lats, lons, global_lats, global_lons)
+    torch = require_cuda()
+
+    effective_cropping_distance = cropping_distance
+    if max_distance_km is not None:
+        # make sure everything outside the crop box is farther than max_distance_km
+        max_lat = max(abs(np.amax(lats)), abs(np.amin(lats)))
+        R_earth_at_lat = R_earth_km * np.cos(np.deg2rad(max_lat))
+        L_1_degree_arc_length_km = R_earth_at_lat * radian
+        max_distance_degrees = max_distance_km / L_1_degree_arc_length_km
+        effective_cropping_distance = max(cropping_distance, 1.1 * max_distance_degrees)
+
+    mask = cropping_mask(global_lats, global_lons, *_crop_box(lats, lons, effective_cropping_distance))
+
+    global_xyz = latlon_to_xyz(global_lats[mask], global_lons[mask])
+    lam_xyz = latlon_to_xyz(lats, lons)
+    n_lam, n_q = lam_xyz[0].shape[0], global_xyz[0].shape[0]
+
+    lam_index = KnnIndex(lam_xyz)
+    if isinstance(min_distance_km, (int, float)):
+        min_distance = min_distance_km / R_earth_km
+    elif min_distance_km == "lam":
+        min_distance = _resolution(lam_index)
+        LOG.info(f"cutout_mask using distance = {min_distance * R_earth_km} km")
+    else:
+        # None / "global" -> resolution of the (cropped) global points (spatial.py:388-393, 104)
+        min_distance = _resolution(global_xyz) if n_q > 0 else float("inf")
+        LOG.info(f"cutout_mask using distance = {min_distance * R_earth_km} km")
+
+    inside_lam = np.zeros((n_q,), dtype=bool)
+    if n_q > 0:
+        if neighbours > n_lam:
+            # cKDTree pads with index n_lam and the reference then indexes lam_points with it
+            raise IndexError(f"index {n_lam} is out of bounds for axis 0 with size {n_lam}")
+        g = tuple(to_device_f64(a) for a in global_xyz)
+        lam = tuple(to_device_f64(a) for a in lam_xyz)
+        idx, dist, _ = lam_index.query(g, k=neighbours)
+        out = torch.empty((n_q,), dtype=torch.uint8, device=idx.device)
+        max_distance = -1.0 if max_distance_km is None else max_distance_km / R_earth_km
+        call(
+            "at_cutout_classify",
+            _ptr(lam[0]), _ptr(lam[1]), _ptr(lam[2]), n_lam,
+            _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), n_q,
+            _ptr(idx), _ptr(dist), int(neighbours),
+            float(min_distance), float(max_distance), int(CUTOUT_DOT_MODE),
+            _ptr(out), stream_ptr(),
+        )  # fmt: skip
+        inside_lam = out.cpu().numpy().astype(bool)
+
+    too_far_mask: bool | NDArray[Any] = False
+    if isinstance(max_distance_km, (int, float)):
+        too_far_mask = ~mask.copy()  # everything outside the cropping area is too far
+
+    mask[mask] = inside_lam
+    mask[too_far_mask] = True
+    mask = ~mask
+
+    if plot:
+        raise NotImplementedError("plotting is not part of this package")
+    return mask
+
+
+def thinning_mask(
+    lats: NDArray[Any],
+    lons: NDArray[Any],
+    global_lats: NDArray[Any],
+    global_lons: NDArray[Any],
+    cropping_distance: float = 2.0,
+) -> NDArray[Any]:
+    """Indices of the LAM points closest to each (cropped) global point (spatial.py:443-503)."""
+    _check_latlon_arrays(lats, lons, global_lats, global_lons)
+    require_cuda()
+    mask = cropping_mask(global_lats, global_lons, *_crop_box(lats, lons, cropping_distance))
+    global_xyz = latlon_to_xyz(global_lats[mask], global_lons[mask])
+    index = KnnIndex(latlon_to_xyz(lats, lons))
+    idx, _, _ = index.query(global_xyz, k=1)
+    return idx[:, 0].cpu().numpy()
+
+
+def global_on_lam_mask(
+    lats: NDArray[Any],
+    lons: NDArray[Any],
+    global_lats: NDArray[Any],
+    global_lons: NDArray[Any],
+    distance_km: float | None = None,
+) -> NDArray[Any]:
+    """Sorted indices of the global points within `distance` of any LAM point (spatial.py:506-536)."""
+    _check_latlon_arrays(lats, lons, global_lats, global_lons)
+    require_cuda()
+    global_index = KnnIndex(latlon_to_xyz(global_lats, global_lons))
+    lam_xyz = latlon_to_xyz(lats, lons)
+    if isinstance(distance_km, (int, float)):
+        distance = distance_km / R_earth_km
+    else:
+        source = KnnIndex(lam_xyz) if distance_km == "lam" else global_index
+        distance = _resolution(source)
+        LOG.info(f"global_on_lam_mask using distance = {distance * R_earth_km} km")
+    mark = global_index.ball_mark(lam_xyz, distance)
+    indices = compact_mask(mark).cpu().numpy()
+    if indices.size == 0:
+        return np.array(sorted(set()))  # the reference's empty result is a float64 array
+    return indices
+
+
+def nearest_grid_points(
+    source_latitudes: NDArray[Any],
+    source_longitudes: NDArray[Any],
+    target_latitudes: NDArray[Any],
+    target_longitudes: NDArray[Any],
+    max_distance: float | None = None,
+    num_neighbours_to_return: int = 1,
+    return_distances: bool = False,
+    _as_device: bool = False,
+    _return_ties: bool = False,
+) -> NDArray[Any] | tuple[NDArray[Any], NDArray[Any]]:
+    """Nearest source grid points of each target point (spatial.py:587-635).
+
+    Indices have shape [n_target] for one neighbour, [n_target, k] otherwise, ascending by
+    distance; with `max_distance` a target with no source strictly inside the bound gets
+    index n_source and distance inf, as cKDTree reports misses.
+    """
+    require_cuda()
+    source_xyz = latlon_to_xyz(source_latitudes, source_longitudes)
+    target_xyz = latlon_to_xyz(target_latitudes, target_longitudes)
+    index = KnnIndex(source_xyz)
+    k = int(num_neighbours_to_return)
+    ub = float("inf") if max_distance is None else float(max_distance)
+    idx, dist, ties = index.query(target_xyz, k=k, distance_upper_bound=ub, want_ties=_return_ties)
+    if k == 1:
+        idx, dist = idx[:, 0], dist[:, 0]
+    if _as_device:
+        return idx
+    indices, distances = idx.cpu().numpy(), dist.cpu().numpy()
+    if _return_ties:
+        return indices, distances, ties.cpu().numpy()
+    if return_distances:
+        return indices, distances
+    return indices

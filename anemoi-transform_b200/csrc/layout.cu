@@ -65,11 +65,12 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-__global__ void compare_mask_kernel(const float* __restrict__ values, size_t stride, long long n,
-                                    int op, float thr, uint8_t* __restrict__ mask) {
+template <typename T>
+__global__ void compare_mask_kernel(const T* __restrict__ values, size_t stride, long long n,
+                                    int op, T thr, uint8_t* __restrict__ mask) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float v = values[static_cast<size_t>(i) * stride];
+    const T v = values[static_cast<size_t>(i) * stride];
     bool m;
     switch (op) {
         case 0: m = v == thr; break;
@@ -147,16 +148,22 @@ extern "C" int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src, 
     return launch_gather<uint2>(idx, n_out, n_src, X, ldx, Y, ldy, n_fields, err_flag, st);
 }
 
-extern "C" int at_compare_mask(const float* values, int64_t stride, int64_t n, int op, float threshold,
-                               uint8_t* mask, void* stream) {
+extern "C" int at_compare_mask(const void* values, int dtype, int64_t stride, int64_t n, int op,
+                               double threshold, uint8_t* mask, void* stream) {
     AT_REQUIRE(values != nullptr && mask != nullptr, "at_compare_mask: null argument");
+    AT_REQUIRE(dtype == AT_F32 || dtype == AT_F64, "at_compare_mask: bad dtype code");
     AT_REQUIRE(op >= 0 && op <= 5, "at_compare_mask: unknown operator %d", op);
     AT_REQUIRE(n >= 0 && stride >= 1, "at_compare_mask: bad shape");
     if (n == 0) return AT_OK;
     const int64_t blocks = (n + 255) / 256;
     AT_REQUIRE(blocks < (1ll << 31), "at_compare_mask: too large");
-    compare_mask_kernel<<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
-        values, static_cast<size_t>(stride), n, op, threshold, mask);
+    if (dtype == AT_F32)
+        // numpy compares a float32 array with a Python scalar in float32 (NEP 50)
+        compare_mask_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            static_cast<const float*>(values), static_cast<size_t>(stride), n, op, static_cast<float>(threshold), mask);
+    else
+        compare_mask_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            static_cast<const double*>(values), static_cast<size_t>(stride), n, op, threshold, mask);
     AT_LAUNCH_CHECK("compare_mask_kernel");
     return AT_OK;
 }

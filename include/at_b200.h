@@ -177,9 +177,10 @@ AT_API int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src,
                    const void* X, int64_t ldx, void* Y, int64_t ldy,
                    int64_t n_fields, int elem_size, int32_t* err_flag, void* stream);
 /* mask[i] = OP(values[i], threshold) — MaskVariable._compute_mask apply_mask.py:160-163.
- * op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.  values: device f32 with element stride `stride`. */
-AT_API int at_compare_mask(const float* values, int64_t stride, int64_t n, int op, float threshold,
-                    uint8_t* mask, void* stream);
+ * op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.  values: device f32 / f64 (dtype) with element
+ * stride `stride`; a float32 array is compared in float32, as numpy does (NEP 50). */
+AT_API int at_compare_mask(const void* values, int dtype, int64_t stride, int64_t n, int op,
+                    double threshold, uint8_t* mask, void* stream);
 
 /* ------------------------------------------------ end-to-end host pipeline ----------- */
 /*

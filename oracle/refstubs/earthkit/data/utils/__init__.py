@@ -1,0 +1,1 @@
+"""Stub package (see oracle/refstubs/README.md)."""

@@ -1,0 +1,129 @@
+"""kNN / ball / compaction parity through the C-ABI against cKDTree (the oracle)."""
+
+import numpy as np
+import pytest
+from scipy.spatial import cKDTree
+
+from anemoi_transform_b200 import synthetic as syn
+from oracle import spatial as osp
+
+pytestmark = pytest.mark.gpu
+
+
+def _xyz(grid):
+    return osp.latlon_to_xyz(*grid)
+
+
+def _check_knn(cuda, src_xyz, tgt_xyz, k, ub=np.inf):
+    """Distances bitwise equal to cKDTree's; indices equal except inside groups of exactly
+    tied d² (where cKDTree's order is its traversal order) — there the sets must agree."""
+    from anemoi_transform_b200.device import KnnIndex
+
+    src, tgt = np.array(src_xyz).T, np.array(tgt_xyz).T
+    d_ref, i_ref = cKDTree(src).query(tgt, k=k, distance_upper_bound=ub)
+    idx, dist, tie = KnnIndex(src_xyz).query(tgt_xyz, k=k, distance_upper_bound=ub, want_ties=True)
+    idx, dist, tie = idx.cpu().numpy(), dist.cpu().numpy(), tie.cpu().numpy()
+    d_ref, i_ref = d_ref.reshape(idx.shape), i_ref.reshape(idx.shape)
+    assert np.array_equal(dist.view(np.uint64), d_ref.view(np.uint64)), "distances differ bitwise"
+    differ = (idx != i_ref).any(axis=1)
+    assert not (differ & (tie == 0)).any(), f"{(differ & (tie == 0)).sum()} untied queries differ"
+    for q in np.nonzero(differ)[0]:
+        # same multiset of indices within the selected set unless the tie straddles the k-th place
+        if not tie[q] & 2:
+            assert sorted(idx[q]) == sorted(i_ref[q]), q
+        # every returned index really is at the reported distance
+        diff = src[idx[q][idx[q] < src.shape[0]]] - tgt[q]
+        d2 = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
+        assert np.array_equal(np.sqrt(d2), dist[q][idx[q] < src.shape[0]])
+    return idx, dist, tie, differ
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 12])
+def test_global_to_global(cuda, k):
+    _check_knn(cuda, _xyz(syn.regular_latlon(1.0)), _xyz(syn.octahedral(96)), k)
+
+
+def test_config2_full_size_bit_exact(cuda):
+    """BASELINE config 2: N320-shaped targets (542,080) vs 0.25° sources (1,038,240), k=1."""
+    idx, dist, tie, differ = _check_knn(cuda, _xyz(syn.regular_latlon(0.25)), _xyz(syn.n320_like()), 1)
+    assert idx.shape == (542_080, 1)
+    assert differ.sum() <= tie.astype(bool).sum() < 200  # exact ties are rare on these grids
+
+
+@pytest.mark.parametrize("k", [1, 5])
+def test_regional_sources_far_queries(cuda, k):
+    """LAM sources, global queries: most queries are far outside the source domain and walk
+    up the grid levels (the brute-force level included)."""
+    _check_knn(cuda, _xyz(syn.rotated_lam(60, 80, 0.05)), _xyz(syn.octahedral(32)), k)
+
+
+def test_upper_bound_is_strict_and_pads(cuda):
+    src, tgt = _xyz(syn.rotated_lam(24, 30, 0.5)), _xyz(syn.octahedral(24))
+    idx, dist, _, _ = _check_knn(cuda, src, tgt, 3, ub=0.01)
+    n = src[0].size
+    assert (idx == n).any() and (idx < n).any() and np.isinf(dist[idx == n]).all()
+    # bound equal to an exact neighbour distance excludes that neighbour (d < bound)
+    from anemoi_transform_b200.device import KnnIndex
+
+    d0 = float(cKDTree(np.array(src).T).query(np.array(tgt).T[:1], k=1)[0][0])
+    i, d, _ = KnnIndex(src).query(tuple(a[:1] for a in tgt), k=1, distance_upper_bound=d0)
+    assert int(i[0, 0]) == n and np.isinf(float(d[0, 0]))
+    i, d, _ = KnnIndex(src).query(tuple(a[:1] for a in tgt), k=1, distance_upper_bound=np.nextafter(d0, 1))
+    assert int(i[0, 0]) < n and float(d[0, 0]) == d0
+
+
+def test_k_larger_than_sources_and_tiny_sets(cuda):
+    from anemoi_transform_b200.device import KnnIndex
+
+    src = (np.array([1.0, 0.0]), np.array([0.0, 1.0]), np.array([0.0, 0.0]))
+    idx, dist, _ = KnnIndex(src).query((np.array([1.0]), np.array([0.0]), np.array([0.0])), k=3)
+    assert idx.cpu().tolist() == [[0, 1, 2]] and dist.cpu()[0, 0] == 0 and np.isinf(float(dist[0, 2]))
+    one = (np.array([0.3]), np.array([0.4]), np.array([0.5]))
+    idx, dist, _ = KnnIndex(one).query(one, k=1)
+    assert idx.cpu().tolist() == [[0]] and float(dist[0, 0]) == 0.0
+    with pytest.raises(ValueError):
+        KnnIndex(one).query(one, k=33)
+
+
+def test_duplicate_points_tie_break_lowest_index(cuda):
+    from anemoi_transform_b200.device import KnnIndex
+
+    x = np.array([0.5, 0.5, 0.5, -0.2])
+    src = (x, x * 0 + 0.1, x * 0 - 0.3)
+    idx, dist, tie = KnnIndex(src).query((np.array([0.5]), np.array([0.1]), np.array([-0.3])), k=2, want_ties=True)
+    assert idx.cpu().tolist() == [[0, 1]] and dist.cpu().tolist() == [[0.0, 0.0]] and int(tie[0]) == 3
+
+
+@pytest.mark.parametrize("r_scale", [0.5, 1.0, 3.7])
+def test_ball_mark_matches_query_ball_point_union(cuda, r_scale):
+    from anemoi_transform_b200.device import KnnIndex, compact_mask
+
+    g, lam = _xyz(syn.octahedral(48)), _xyz(syn.rotated_lam(30, 40, 0.3))
+    gp, lp = np.array(g).T, np.array(lam).T
+    r = osp.resolution(gp) * r_scale
+    want = np.array(sorted(set(i for sub in cKDTree(gp).query_ball_point(lp, r) for i in sub)))
+    got = compact_mask(KnnIndex(g).ball_mark(lam, r)).cpu().numpy()
+    assert got.dtype == np.int64 and np.array_equal(got, want)
+
+
+def test_min_nn_distance_is_resolution(cuda):
+    from anemoi_transform_b200.device import KnnIndex
+
+    for grid in (syn.octahedral(32), syn.rotated_lam(40, 50, 0.02), syn.regular_latlon(2.0)):
+        xyz = _xyz(grid)
+        assert KnnIndex(xyz).min_nn_distance() == osp.resolution(np.array(xyz).T)
+
+
+def test_compact_and_cropping(cuda, golden_spatial):
+    from anemoi_transform_b200.device import compact_mask, cropping_mask_device
+
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15, 16, 17, 4095, 4096, 4097, 100_003):
+        m = (rng.uniform(size=n) < 0.3).astype(np.uint8) * rng.integers(1, 255, n).astype(np.uint8)
+        got = compact_mask(cuda.from_numpy(m).cuda()).cpu().numpy() if n else np.zeros(0, np.int64)
+        assert np.array_equal(got, np.nonzero(m)[0])
+    g = golden_spatial
+    got = cropping_mask_device(g["g_lat"], g["g_lon"], 70.0, -20.0, 40.0, 15.0).cpu().numpy().astype(bool)
+    assert np.array_equal(got, g["crop_wrap"])
+    got = cropping_mask_device(g["g_lat"], g["g_lon"] - 360.0, 10.0, 100.0, -10.0, 140.0).cpu().numpy().astype(bool)
+    assert np.array_equal(got, g["crop_plus360"])

@@ -1,0 +1,113 @@
+"""The drop-in spatial functions against the imported reference's golden outputs, the
+reference's known-answer tests and the oracle on mid-size grids."""
+
+import numpy as np
+import pytest
+
+from anemoi_transform_b200 import synthetic as syn
+from oracle import spatial as osp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp(cuda):
+    from anemoi_transform_b200 import spatial
+
+    return spatial
+
+
+def _lam11():
+    la, lo = np.meshgrid(np.linspace(44.0, 46.0, 11), np.linspace(0.0, 2.0, 11))
+    return la.flatten(), lo.flatten()
+
+
+# ---- reference tests/test_spatial.py ported verbatim in spirit -------------------------------
+@pytest.mark.parametrize("cropping_distance", [1.0, 3.0, 5.0])
+def test_cutout_mask_with_max_distance(sp, cropping_distance):
+    lam_lats, lam_lons = _lam11()
+    mask = sp.cutout_mask(lam_lats, lam_lons, np.array([43.1, 44.0, 45.0, 45.5, 46.0, 50.0]), np.array([359.1, 359.5, 0.0, 1.0, 2.0, 0.0]), cropping_distance=cropping_distance, max_distance_km=250.0)
+    assert isinstance(mask, np.ndarray) and mask.shape == (6,)
+    assert np.array_equal(mask, np.array([True, False, False, False, False, False]))
+
+
+def test_cutout_mask_with_min_distance(sp):
+    lam_lats, lam_lons = _lam11()
+    mask = sp.cutout_mask(lam_lats, lam_lons, np.array([44.0, 45.0, 46.0, 46.1, 47.5]), np.array([0.0, 1.0, 2.0, -0.1, -1.5]), min_distance_km=100.0)
+    assert np.array_equal(mask, np.array([False, False, False, False, True]))
+
+
+def test_cutout_mask_array_shapes(sp):
+    with pytest.raises(AssertionError):
+        sp.cutout_mask(np.array([[45.0, 45.0], [46.0, 46.0]]), np.array([[0.0, 1.0], [0.0, 1.0]]), np.array([45.0]), np.array([0.0]))
+
+
+def test_cutout_mask_parameter_types(sp):
+    lam_lats, lam_lons = _lam11()
+    g = (np.array([45.0, 46.0]), np.array([0.0, 2.0]))
+    assert isinstance(sp.cutout_mask(lam_lats, lam_lons, *g, max_distance_km=100), np.ndarray)
+    assert isinstance(sp.cutout_mask(lam_lats, lam_lons, *g, max_distance_km=100.0), np.ndarray)
+    with pytest.raises(AssertionError, match="neighbours must be positive"):
+        sp.cutout_mask(lam_lats, lam_lons, *g, neighbours=0)
+    with pytest.raises(AssertionError, match="cropping_distance must be non-negative"):
+        sp.cutout_mask(lam_lats, lam_lons, *g, cropping_distance=-1.0)
+
+
+def test_cutout_mask_large_grid(sp):
+    la, lo = np.meshgrid(np.linspace(40.0, 50.0, 21), np.linspace(0.0, 10.0, 21))
+    gla, glo = np.meshgrid(np.linspace(30.0, 60.0, 31), np.linspace(-10.0, 20.0, 31))
+    args = (la.flatten(), lo.flatten(), gla.flatten(), glo.flatten())
+    mask = sp.cutout_mask(*args, min_distance_km=150.0, max_distance_km=300.0)
+    assert mask.shape == (961,) and mask.dtype == bool and np.any(mask) and not np.all(mask)
+    assert np.array_equal(mask, osp.cutout_mask(*args, min_distance_km=150.0, max_distance_km=300.0))
+
+
+# ---- golden outputs of the imported reference -----------------------------------------------
+def test_golden_nearest_grid_points(sp, golden_spatial):
+    g = golden_spatial
+    idx = sp.nearest_grid_points(g["g_lat"], g["g_lon"], g["o_lat"], g["o_lon"])
+    assert idx.dtype == np.int64 and idx.shape == g["ngp_k1"].shape
+    i_t, d_t, ties = sp.nearest_grid_points(g["g_lat"], g["g_lon"], g["o_lat"], g["o_lon"], _return_ties=True)
+    assert not ((idx != g["ngp_k1"]) & (ties == 0)).any()
+    i4, d4 = sp.nearest_grid_points(g["g_lat"], g["g_lon"], g["lam_lat"], g["lam_lon"], num_neighbours_to_return=4, return_distances=True)
+    assert np.array_equal(d4, g["ngp_k4_dist"]) and i4.shape == (720, 4)
+    assert np.array_equal(i4, g["ngp_k4_idx"])  # rotated LAM vs lat-lon grid: no exact ties
+    iu, du = sp.nearest_grid_points(g["lam_lat"], g["lam_lon"], g["o_lat"], g["o_lon"], max_distance=0.01, return_distances=True)
+    assert np.array_equal(iu, g["ngp_ub_idx"]) and np.array_equal(du, g["ngp_ub_dist"])
+
+
+def test_golden_masks(sp, golden_spatial):
+    g = golden_spatial
+    lam, o = (g["lam_lat"], g["lam_lon"]), (g["o_lat"], g["o_lon"])
+    assert np.array_equal(sp.cropping_mask(g["g_lat"], g["g_lon"], 70.0, -20.0, 40.0, 15.0), g["crop_wrap"])
+    t = sp.thinning_mask(*lam, *o)
+    assert t.dtype == np.int64 and np.array_equal(t, g["thinning"])
+    assert np.array_equal(sp.thinning_mask(*lam, g["g_lat"], g["g_lon"], cropping_distance=6.0), g["thinning_crop6"])
+    m = sp.global_on_lam_mask(*lam, *o)
+    assert m.dtype == np.int64 and np.array_equal(m, g["gol_none"])
+    assert np.array_equal(sp.global_on_lam_mask(*lam, *o, distance_km=150.0), g["gol_150km"])
+    empty = sp.global_on_lam_mask(*lam, *o, distance_km=1.0)
+    assert empty.shape == (0,) and empty.dtype == np.float64
+
+
+@pytest.mark.parametrize("dot_mode", [1, 0])
+def test_golden_cutout(sp, golden_spatial, dot_mode, monkeypatch):
+    monkeypatch.setattr(sp, "CUTOUT_DOT_MODE", dot_mode)
+    g = golden_spatial
+    lam, o = (g["lam_lat"], g["lam_lon"]), (g["o_lat"], g["o_lon"])
+    assert np.array_equal(sp.cutout_mask(*lam, *o), g["cutout_default"])
+    assert np.array_equal(sp.cutout_mask(*lam, *o, min_distance_km=80.0, max_distance_km=400.0), g["cutout_min80_max400"])
+    assert np.array_equal(sp.cutout_mask(*lam, *o, cropping_distance=5.0, neighbours=3, min_distance_km=10), g["cutout_n3_crop5"])
+    assert np.array_equal(sp.cutout_mask(*lam, g["g_lat"], g["g_lon"]), g["cutout_regular_default"])
+
+
+# ---- mid-size grids against the oracle -----------------------------------------------------
+def test_midsize_lam_in_global(sp):
+    """A 200x240 LAM at 0.05° inside O160: cutout / thinning / global-on-lam against the oracle."""
+    lam = syn.rotated_lam(200, 240, 0.05, 55.0, 15.0)
+    glob = syn.octahedral(160)
+    assert np.array_equal(sp.cutout_mask(*lam, *glob), osp.cutout_mask_vectorised(*lam, *glob))
+    assert np.array_equal(sp.cutout_mask(*lam, *glob, min_distance_km=20, max_distance_km=150), osp.cutout_mask_vectorised(*lam, *glob, min_distance_km=20, max_distance_km=150))
+    assert np.array_equal(sp.thinning_mask(*lam, *glob), osp.thinning_mask(*lam, *glob))
+    assert np.array_equal(sp.global_on_lam_mask(*lam, *glob), osp.global_on_lam_mask(*lam, *glob))
+    assert np.array_equal(sp.global_on_lam_mask(*lam, *glob, distance_km=40.0), osp.global_on_lam_mask(*lam, *glob, distance_km=40.0))
