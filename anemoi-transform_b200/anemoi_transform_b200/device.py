@@ -374,7 +374,7 @@ class DeviceBatch:
 class HostPipeline:
     """Streaming regrid of host-resident fields (at_pipeline_*)."""
 
-    def __init__(self, csr: CsrMatrix, chunk_fields: int = 128):
+    def __init__(self, csr: CsrMatrix, chunk_fields: int = 64):
         require_cuda()
         self.csr = csr
         h = c_void_p()

@@ -119,9 +119,14 @@ extern "C" int at_pipeline_regrid(at_pipeline_t* p, const float* const* fields_i
         const int nf = static_cast<int>(std::min<int64_t>(p->chunk, n_fields - f0));
         // stage in: the buffer is free once the pack of chunk c - kBuffers has read it
         if (c >= kBuffers) AT_CUDA_TRY(cudaStreamWaitEvent(p->s_in, p->packed[b], 0));
-        for (int f = 0; f < nf; ++f)
-            AT_CUDA_TRY(cudaMemcpyAsync(p->d_in[b] + static_cast<size_t>(f) * p->n_src, fields_in[f0 + f], src_bytes,
-                                        cudaMemcpyHostToDevice, p->s_in));
+        // fields that are adjacent in host memory (one [F, n] array) go in one copy
+        for (int f = 0; f < nf;) {
+            int g = f + 1;
+            while (g < nf && fields_in[f0 + g] == fields_in[f0 + g - 1] + p->n_src) ++g;
+            AT_CUDA_TRY(cudaMemcpyAsync(p->d_in[b] + static_cast<size_t>(f) * p->n_src, fields_in[f0 + f],
+                                        src_bytes * static_cast<size_t>(g - f), cudaMemcpyHostToDevice, p->s_in));
+            f = g;
+        }
         AT_CUDA_TRY(cudaEventRecord(p->h2d_done[b], p->s_in));
 
         // compute
@@ -139,9 +144,13 @@ extern "C" int at_pipeline_regrid(at_pipeline_t* p, const float* const* fields_i
 
         // drain
         AT_CUDA_TRY(cudaStreamWaitEvent(p->s_out, p->computed[b], 0));
-        for (int f = 0; f < nf; ++f)
+        for (int f = 0; f < nf;) {
+            int g = f + 1;
+            while (g < nf && fields_out[f0 + g] == fields_out[f0 + g - 1] + p->n_tgt) ++g;
             AT_CUDA_TRY(cudaMemcpyAsync(fields_out[f0 + f], p->d_out[b] + static_cast<size_t>(f) * p->n_tgt,
-                                        tgt_bytes, cudaMemcpyDeviceToHost, p->s_out));
+                                        tgt_bytes * static_cast<size_t>(g - f), cudaMemcpyDeviceToHost, p->s_out));
+            f = g;
+        }
         AT_CUDA_TRY(cudaEventRecord(p->drained[b], p->s_out));
     }
     cudaError_t e1 = cudaStreamSynchronize(p->s_in);

@@ -30,6 +30,8 @@ struct at_csr {
     int data_dtype = AT_F32;
     int uniform_nnz = 0;
     int max_row_nnz = 0;
+    int max_seg64 = 0;  // largest number of entries in any aligned block of 64 rows
+    double live_cols = 0;  // average number of source columns between their first and last use
     int32_t* d_indptr = nullptr;   // n_rows + 1 (+ padding)
     int32_t* d_indices = nullptr;  // nnz (+ padding)
     void* d_data = nullptr;        // nnz float or double (+ padding)
@@ -89,6 +91,7 @@ struct SpmmArgs {
     int n_rows;
     int n_vec;          // F / 4 (float4 columns), rounded up
     int rows_per_cta;
+    int super;          // column tiles per super-tile: blockIdx.x walks (row block, tile in super-tile)
 };
 
 __device__ __forceinline__ float4 mul_add_rn(float4 acc, float w, float4 x) {
@@ -101,7 +104,7 @@ __device__ __forceinline__ float4 mul_add_rn(float4 acc, float w, float4 x) {
 
 // Stage the CTA's CSR segment in shared memory.  Returns the base entry (segment start).
 // UNNZ > 0: uniform row length, regular tile -> bulk async copy when BULK.
-template <int UNNZ, bool BULK>
+template <int UNNZ, bool BULK, bool FALLBACK>
 __device__ __forceinline__ void stage_segment(const SpmmArgs& a, int r0, int nrows, int* s_ptr,
                                               int* s_idx, float* s_w, uint64_t* s_bar,
                                               int& seg_base, bool& in_smem) {
@@ -137,7 +140,8 @@ __device__ __forceinline__ void stage_segment(const SpmmArgs& a, int r0, int nro
         __syncthreads();
         seg_base = s_ptr[0];
         const int len = s_ptr[nrows] - seg_base;
-        in_smem = len <= kSegCap;
+        // without FALLBACK the host has checked that every CTA's segment fits (max_seg64)
+        in_smem = !FALLBACK || len <= kSegCap;
         if (in_smem) {
             for (int i = tid; i < len; i += kThreads) {
                 s_idx[i] = __ldg(a.indices + seg_base + i);
@@ -188,28 +192,32 @@ __device__ __forceinline__ void accumulate_row(const SpmmArgs& a, int p0, int p1
     }
 }
 
-template <int VPL, int UNNZ, bool BULK>
+template <int VPL, int UNNZ, bool BULK, bool FALLBACK>
 __global__ void __launch_bounds__(kThreads) spmm_f32_kernel(const SpmmArgs a) {
     __shared__ __align__(16) int s_idx[kSegCap];
     __shared__ __align__(16) float s_w[kSegCap];
     __shared__ int s_ptr[kMaxRowsPerCta + 1];
     __shared__ __align__(8) uint64_t s_bar;
 
-    const int r0 = blockIdx.x * a.rows_per_cta;
+    // blockIdx.x = row_block * super + tile_in_super: CTAs that run together cover `super`
+    // adjacent column tiles of the same rows, i.e. super·VPL·512 contiguous bytes per source row.
+    const int tile = blockIdx.y * a.super + static_cast<int>(blockIdx.x % a.super);
+    const int r0 = static_cast<int>(blockIdx.x / a.super) * a.rows_per_cta;
     const int nrows = min(a.rows_per_cta, a.n_rows - r0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (tile * (kWarp * VPL) >= a.n_vec) return;
 
     int vcol[VPL];
     bool vok[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
-        vcol[v] = blockIdx.y * (kWarp * VPL) + v * kWarp + lane;
+        vcol[v] = tile * (kWarp * VPL) + v * kWarp + lane;
         vok[v] = vcol[v] < a.n_vec;
     }
 
     int seg_base;
     bool in_smem;
-    stage_segment<UNNZ, BULK>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
+    stage_segment<UNNZ, BULK, FALLBACK>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
 
     for (int lr = warp; lr < nrows; lr += kWarps) {
         float4 acc[VPL];
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(kThreads) spmm_f32_kernel(const SpmmArgs a) {
         if constexpr (UNNZ > 0) {
             accumulate_row<VPL, (UNNZ < 4 ? UNNZ : 4), true>(a, lr * UNNZ, (lr + 1) * UNNZ, s_idx,
                                                              s_w, vcol, vok, acc);
-        } else if (in_smem) {
+        } else if (!FALLBACK || in_smem) {
             accumulate_row<VPL, 4, true>(a, s_ptr[lr] - seg_base, s_ptr[lr + 1] - seg_base, s_idx,
                                          s_w, vcol, vok, acc);
         } else {
@@ -243,6 +251,7 @@ struct FusedArgs {
     size_t ldy;  // in floats
 };
 
+template <int UNNZ, bool FALLBACK>
 __global__ void __launch_bounds__(kThreads) spmm_fused_kernel(const FusedArgs f) {
     __shared__ __align__(16) int s_idx[kSegCap];
     __shared__ __align__(16) float s_w[kSegCap];
@@ -260,11 +269,13 @@ __global__ void __launch_bounds__(kThreads) spmm_fused_kernel(const FusedArgs f)
 
     int seg_base;
     bool in_smem;
-    stage_segment<0, false>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
+    stage_segment<UNNZ, UNNZ != 0, FALLBACK>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
 
     for (int lr = warp; lr < nrows; lr += kWarps) {
         float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
-        if (in_smem) {
+        if constexpr (UNNZ > 0) {
+            accumulate_row<1, 4, true>(a, lr * UNNZ, (lr + 1) * UNNZ, s_idx, s_w, vcol, vok, acc);
+        } else if (!FALLBACK || in_smem) {
             accumulate_row<1, 4, true>(a, s_ptr[lr] - seg_base, s_ptr[lr + 1] - seg_base, s_idx,
                                        s_w, vcol, vok, acc);
         } else {
@@ -358,17 +369,25 @@ static int launch_generic(const at_csr* csr, const void* X, int64_t ldx, void* Y
 template <int VPL>
 static int launch_f32(const at_csr* csr, const SpmmArgs& args, bool bulk, bool force_general,
                       cudaStream_t st) {
-    const unsigned gx = static_cast<unsigned>((csr->n_rows + args.rows_per_cta - 1) / args.rows_per_cta);
-    const unsigned gy = static_cast<unsigned>((args.n_vec + kWarp * VPL - 1) / (kWarp * VPL));
-    if (gy > 65535u) return set_error(AT_ERR_UNSUPPORTED, "too many column tiles (%u)", gy);
-    dim3 grid(gx, gy);
-    const bool uniform4 = !force_general && csr->uniform_nnz == 4;
-    if (uniform4 && bulk)
-        spmm_f32_kernel<VPL, 4, true><<<grid, kThreads, 0, st>>>(args);
-    else if (uniform4)
-        spmm_f32_kernel<VPL, 4, false><<<grid, kThreads, 0, st>>>(args);
+    const int64_t row_blocks = (csr->n_rows + args.rows_per_cta - 1) / args.rows_per_cta;
+    const int64_t tiles = (args.n_vec + kWarp * VPL - 1) / (kWarp * VPL);
+    const int64_t gx64 = row_blocks * args.super, gy64 = (tiles + args.super - 1) / args.super;
+    if (gy64 > 65535 || gx64 >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "grid too large");
+    dim3 grid(static_cast<unsigned>(gx64), static_cast<unsigned>(gy64));
+    const int u = force_general ? 0 : csr->uniform_nnz;
+    const bool fits = csr->max_seg64 <= kSegCap;
+    if (u == 4 && bulk)
+        spmm_f32_kernel<VPL, 4, true, false><<<grid, kThreads, 0, st>>>(args);
+    else if (u == 4)
+        spmm_f32_kernel<VPL, 4, false, false><<<grid, kThreads, 0, st>>>(args);
+    else if (u == 12 && VPL <= 2 && bulk)
+        spmm_f32_kernel<(VPL <= 2 ? VPL : 1), 12, true, false><<<grid, kThreads, 0, st>>>(args);
+    else if (u == 12 && VPL <= 2)
+        spmm_f32_kernel<(VPL <= 2 ? VPL : 1), 12, false, false><<<grid, kThreads, 0, st>>>(args);
+    else if (fits)
+        spmm_f32_kernel<VPL, 0, false, false><<<grid, kThreads, 0, st>>>(args);
     else
-        spmm_f32_kernel<VPL, 0, false><<<grid, kThreads, 0, st>>>(args);
+        spmm_f32_kernel<VPL, 0, false, true><<<grid, kThreads, 0, st>>>(args);
     AT_LAUNCH_CHECK("spmm_f32_kernel");
     return AT_OK;
 }
@@ -437,6 +456,28 @@ extern "C" int at_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const 
     }
     c->uniform_nnz = uniform;
     c->max_row_nnz = max_nnz;
+    for (int64_t r = 0; r < n_rows; r += kMaxRowsPerCta) {
+        const int64_t e = std::min<int64_t>(n_rows, r + kMaxRowsPerCta);
+        c->max_seg64 = std::max(c->max_seg64, h_ptr[static_cast<size_t>(e)] - h_ptr[static_cast<size_t>(r)]);
+    }
+    {
+        // Reuse working set: a source column is "live" between the first and the last target
+        // row that references it; the mean number of live columns while the rows are walked in
+        // order is sum(span) / n_rows.  at_spmm sizes its column super-tile so that the live
+        // source rows of the CTAs in flight stay in L2.
+        std::vector<int32_t> first(static_cast<size_t>(n_cols), -1), last(static_cast<size_t>(n_cols), -1);
+        for (int64_t r = 0; r < n_rows; ++r)
+            for (int32_t p = h_ptr[static_cast<size_t>(r)]; p < h_ptr[static_cast<size_t>(r + 1)]; ++p) {
+                const size_t col = static_cast<size_t>(h_idx[static_cast<size_t>(p)]);
+                if (first[col] < 0) first[col] = static_cast<int32_t>(r);
+                last[col] = static_cast<int32_t>(r);
+            }
+        double span = 0;
+        for (int64_t col = 0; col < n_cols; ++col)
+            if (first[static_cast<size_t>(col)] >= 0)
+                span += static_cast<double>(last[static_cast<size_t>(col)] - first[static_cast<size_t>(col)] + 1);
+        c->live_cols = n_rows > 0 ? span / static_cast<double>(n_rows) : 0.0;
+    }
     cudaGetDevice(&c->device);
 
     const size_t esz = data_dtype == AT_F32 ? 4 : 8;
@@ -488,15 +529,17 @@ extern "C" int at_csr_info(const at_csr_t* c, int64_t* n_rows, int64_t* n_cols, 
     return AT_OK;
 }
 
-static int decode_variant(int variant, int& vpl, int& rows_per_warp, bool& bulk, bool& general) {
+static int decode_variant(int variant, int& vpl, int& rows_per_warp, bool& bulk, bool& general, int& super) {
     // bits 0-2: float4 per lane per nonzero (1, 2, 4); bits 4-7: rows per warp;
-    // bit 8: bulk-copy (TMA) staging off; bit 9: force the general-CSR kernel.
+    // bit 8: bulk-copy (TMA) staging off; bit 9: force the general-CSR kernel;
+    // bits 12-17: column tiles per super-tile.
     vpl = variant & 7;
     rows_per_warp = (variant >> 4) & 15;
     bulk = ((variant >> 8) & 1) == 0;
     general = ((variant >> 9) & 1) != 0;
+    super = (variant >> 12) & 63;  // 0: chosen from the matrix's reuse working set
     if (vpl == 0) vpl = 2;
-    if (rows_per_warp == 0) rows_per_warp = 4;
+    if (rows_per_warp == 0) rows_per_warp = 8;
     if (vpl != 1 && vpl != 2 && vpl != 4)
         return set_error(AT_ERR_INVALID, "at_spmm: variant selects %d float4 per lane", vpl);
     if (rows_per_warp * kWarps > kMaxRowsPerCta)
@@ -521,9 +564,9 @@ extern "C" int at_spmm(const at_csr_t* csr, const void* X, int x_dtype, int64_t 
         AT_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0, "at_spmm: ldx, ldy must be multiples of 4");
         AT_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
                    "at_spmm: X and Y must be 16-byte aligned");
-        int vpl, rpw;
+        int vpl, rpw, super;
         bool bulk, general;
-        int rc = decode_variant(spmm_variant, vpl, rpw, bulk, general);
+        int rc = decode_variant(spmm_variant, vpl, rpw, bulk, general, super);
         if (rc != AT_OK) return rc;
         SpmmArgs a;
         a.indptr = csr->d_indptr;
@@ -537,6 +580,19 @@ extern "C" int at_spmm(const at_csr_t* csr, const void* X, int x_dtype, int64_t 
         // Columns beyond n_fields up to the next multiple of 4 are padding inside ld.
         a.n_vec = static_cast<int>((n_fields + 3) / 4);
         a.rows_per_cta = rpw * kWarps;
+        if (csr->uniform_nnz > 0 && !general)  // the staged segment of a CTA must fit
+            a.rows_per_cta = std::max(kWarps, std::min(a.rows_per_cta, kSegCap / csr->uniform_nnz / kWarps * kWarps));
+        const int tiles = (a.n_vec + kWarp * vpl - 1) / (kWarp * vpl);
+        if (super == 0) {
+            // Widest super-tile (most contiguous bytes per source row, best DRAM page locality)
+            // whose live source rows stay in L2.  Rows being streamed by the resident CTAs
+            // roughly double the set that has to survive until its last use; 64 MB is half of
+            // the B200's L2.
+            const double l2_budget = 64.0e6;
+            const double tile_bytes = 512.0 * vpl;
+            super = static_cast<int>(l2_budget / (2.0 * std::max(1.0, csr->live_cols) * tile_bytes));
+        }
+        a.super = std::max(1, std::min({super, tiles, 63}));
         switch (vpl) {
             case 1: return launch_f32<1>(csr, a, bulk, general, st);
             case 2: return launch_f32<2>(csr, a, bulk, general, st);
@@ -650,6 +706,7 @@ extern "C" int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi, cons
     f.s.n_rows = static_cast<int>(csr->n_rows);
     f.s.n_vec = 0;
     f.s.rows_per_cta = 4 * kWarps;
+    f.s.super = 1;
     f.tiles = epi->d_tiles;
     f.cols = epi->d_cols32;
     f.row_mask = row_mask;
@@ -657,7 +714,14 @@ extern "C" int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi, cons
     f.ldy = static_cast<size_t>(ldy);
     dim3 grid(static_cast<unsigned>((csr->n_rows + f.s.rows_per_cta - 1) / f.s.rows_per_cta),
               static_cast<unsigned>(epi->n_tiles));
-    spmm_fused_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(f);
+    if (csr->uniform_nnz == 4)
+        spmm_fused_kernel<4, false><<<grid, kThreads, 0, as_stream(stream)>>>(f);
+    else if (csr->uniform_nnz == 12)
+        spmm_fused_kernel<12, false><<<grid, kThreads, 0, as_stream(stream)>>>(f);
+    else if (csr->max_seg64 <= kSegCap)
+        spmm_fused_kernel<0, false><<<grid, kThreads, 0, as_stream(stream)>>>(f);
+    else
+        spmm_fused_kernel<0, true><<<grid, kThreads, 0, as_stream(stream)>>>(f);
     AT_LAUNCH_CHECK("spmm_fused_kernel");
     return AT_OK;
 }

@@ -258,6 +258,13 @@ def run_gpu(args):
             ref = m @ X[:, col].cpu().numpy()
             parity = parity and bool(np.array_equal(ref.view(np.uint32), Y[:, col].cpu().numpy().view(np.uint32)))
 
+    if args.value_only:
+        if rank == 0:
+            print(json.dumps({"metric": "regrid_fields_per_s", "value": value, "unit": "fields/s", "ms_per_step": ms_per_step, "partial": "--value-only", "roofline": {"achieved": achieved, "peak": peak, "frac": achieved / peak}, "parity_spot_check": parity}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- kNN (config 2) ---------------------------------------------------------------------
     from anemoi_transform_b200 import spatial
     from anemoi_transform_b200 import synthetic as syn
@@ -406,8 +413,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="at_spmm kernel shape (0 = default)")
-    ap.add_argument("--chunk", type=int, default=128, help="fields per chunk of the host pipeline")
+    ap.add_argument("--chunk", type=int, default=64, help="fields per chunk of the host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--value-only", action="store_true", help="device-resident leg only (for ncu captures); prints a partial line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)
     if args.impl == "reference":
