@@ -253,9 +253,10 @@ class KnnIndex:
         call("at_ball_mark", self._h, _ptr(qx), _ptr(qy), _ptr(qz), int(qx.shape[0]), float(r), _ptr(mark), stream_ptr())
         return mark
 
-    def min_nn_distance(self) -> float:
+    def min_nn_distance(self, first: int = 0, count: int = -1) -> float:
+        """min over sources [first, first+count) of the distance to their 2nd nearest source."""
         out = c_double()
-        call("at_min_nn_distance", self._h, byref(out), stream_ptr())
+        call("at_min_nn_distance", self._h, int(first), int(count), byref(out), stream_ptr())
         return out.value
 
 

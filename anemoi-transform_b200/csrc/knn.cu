@@ -434,11 +434,11 @@ __global__ void __launch_bounds__(256)
 
 // min over sources of the distance to the 2nd nearest source (k = 2 self query).
 __global__ void __launch_bounds__(256)
-    min_second_nn_kernel(const KnnDev d, unsigned long long* __restrict__ out_bits) {
+    min_second_nn_kernel(const KnnDev d, long long first, long long end, unsigned long long* __restrict__ out_bits) {
     const int lane = threadIdx.x & 31;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     double best = INFINITY;
-    for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < d.n; q += warps) {
+    for (long long q = first + ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5); q < end; q += warps) {
         double d2;
         long long idx;
         knn_one(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d2, idx);
@@ -728,8 +728,15 @@ extern "C" int at_ball_mark(const at_knn_t* k, const double* qx, const double* q
     return AT_OK;
 }
 
-extern "C" int at_min_nn_distance(const at_knn_t* k, double* out_host, void* stream) {
+extern "C" int at_min_nn_distance(const at_knn_t* k, int64_t first, int64_t count, double* out_host,
+                                  void* stream) {
     AT_REQUIRE(k != nullptr && out_host != nullptr, "at_min_nn_distance: null argument");
+    AT_REQUIRE(first >= 0 && first <= k->n, "at_min_nn_distance: first out of range");
+    const long long end = count < 0 ? k->n : std::min<long long>(k->n, first + count);
+    if (end <= first) {
+        *out_host = INFINITY;
+        return AT_OK;
+    }
     unsigned long long* d_bits = nullptr;
     AT_CUDA_TRY(cudaMalloc(&d_bits, 8));
     const double inf = INFINITY;
@@ -738,7 +745,7 @@ extern "C" int at_min_nn_distance(const at_knn_t* k, double* out_host, void* str
     cudaStream_t st = as_stream(stream);
     cudaError_t e = cudaMemcpyAsync(d_bits, &init, 8, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
-        min_second_nn_kernel<<<query_blocks(k->n), 256, 0, st>>>(k->dev, d_bits);
+        min_second_nn_kernel<<<query_blocks(end - first), 256, 0, st>>>(k->dev, first, end, d_bits);
         e = cudaGetLastError();
     }
     unsigned long long bits = init;

@@ -227,9 +227,11 @@ AT_API int at_knn_query(const at_knn_t* knn, const double* qx, const double* qy,
  */
 AT_API int at_ball_mark(const at_knn_t* knn, const double* qx, const double* qy, const double* qz,
                  int64_t nq, double r, uint8_t* mark, void* stream);
-/* out_host = min over sources of the distance to their 2nd nearest source (self included
- * as the 1st) — `_resolution`  spatial.py:93-97.  Synchronises the stream. */
-AT_API int at_min_nn_distance(const at_knn_t* knn, double* out_host, void* stream);
+/* out_host = min over sources [first, first+count) of the distance to their 2nd nearest
+ * source (self included as the 1st) — `_resolution`  spatial.py:93-97; count < 0 means
+ * "to the end" (ranks take sub-ranges and all-reduce MIN).  Synchronises the stream. */
+AT_API int at_min_nn_distance(const at_knn_t* knn, int64_t first, int64_t count, double* out_host,
+                       void* stream);
 /* Sorted indices of the non-zero bytes of mark[n] (stream compaction):
  * `np.array(sorted(set(...)))` spatial.py:534 / boolean-mask selection.
  * out_idx: device int64[n] (capacity n); *count_host receives the count. Synchronises. */
