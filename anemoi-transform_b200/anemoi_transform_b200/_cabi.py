@@ -62,6 +62,7 @@ PROTOTYPES = {
     "at_pointwise": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "at_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "at_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
+    "at_gather_cols": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "at_compare_mask": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p]),
     "at_pipeline_create": (c_int, [c_void_p, c_int32, POINTER(c_void_p)]),
     "at_pipeline_destroy": (c_int, [c_void_p]),

@@ -6,7 +6,7 @@ from typing import Any, Sequence
 
 import numpy as np
 
-from .device import DeviceBatch, require_cuda, round_up
+from .device import DeviceBatch, gather_cols, require_cuda, round_up
 from .fields import device_column_of
 
 
@@ -29,14 +29,20 @@ def fields_to_batch(fields: Sequence[Any]) -> DeviceBatch:
             return DeviceBatch(first_batch.data[:, c0 : c0 + round_up(n, 4)], n)
         dtypes = {c[0].data.dtype for c in cols}
         if len(dtypes) == 1 and len({c[0].n_points for c in cols}) == 1:
-            ld = round_up(n, 4)
-            out = torch.zeros((first_batch.n_points, ld), dtype=first_batch.data.dtype, device=first_batch.data.device)
-            if len(batches) == 1:
-                index = torch.tensor([c[1] for c in cols], device=out.device, dtype=torch.int64)
-                out[:, :n] = first_batch.data.index_select(1, index)
+            out = torch.zeros((first_batch.n_points, round_up(n, 4)), dtype=first_batch.data.dtype, device=first_batch.data.device)
+            # one column-gather launch per source batch, each writing its own output columns
+            by_batch: dict[int, list[tuple[int, int]]] = {}
+            for j, (b, c) in enumerate(cols):
+                by_batch.setdefault(id(b), []).append((j, c))
+            lookup = {id(c[0]): c[0] for c in cols}
+            if len(by_batch) == 1:
+                gather_cols(first_batch.data, [c[1] for c in cols], out=out)
             else:
-                for j, (b, c) in enumerate(cols):
-                    out[:, j] = b.data[:, c]
+                for key, pairs in by_batch.items():
+                    tmp = gather_cols(lookup[key].data, [c for _, c in pairs])
+                    # scatter this batch's columns to their places (contiguous runs in practice)
+                    for k, (j, _) in enumerate(pairs):
+                        out[:, j] = tmp[:, k]
             return DeviceBatch(out, n)
     return DeviceBatch.from_host_fields([f.to_numpy(flatten=True) for f in fields])
 

@@ -312,6 +312,19 @@ def gather_rows(X, idx, n_fields: int | None = None, out=None):
     return out
 
 
+def gather_cols(X, cols: Sequence[int], out=None):
+    """out[:, j] = X[:, cols[j]] — regroup the fields of a resident point-major batch."""
+    torch = _torch()
+    n_out = len(cols)
+    if any(c < 0 or c >= X.shape[1] for c in cols):
+        raise IndexError("column index out of range")
+    if out is None:
+        out = torch.zeros((X.shape[0], round_up(n_out, 4)), dtype=X.dtype, device=X.device)
+    index = torch.tensor(list(cols), dtype=torch.int32, device=X.device)
+    call("at_gather_cols", _ptr(index), n_out, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), X.element_size(), stream_ptr())
+    return out
+
+
 def compare_mask(values, op: int, threshold: float):
     """uint8 mask = OP(values, threshold) for a 1-D (possibly strided) float CUDA tensor."""
     torch = _torch()

@@ -24,9 +24,22 @@ class Pipeline(Workflow):
 
     def __init__(self, *, filters: list[Any]) -> None:
         self.filters = filters
+        self._plan: list[Any] | None = None
+        self._plan_key: tuple[int, ...] = ()
+
+    def execution_plan(self) -> list[Any]:
+        """The filters as they will run forward: nested pipelines flattened and
+        `regrid | pointwise…` runs fused into one launch (see fusion.py).  Results are
+        those of running `self.filters` one after the other."""
+        from .fusion import flatten, fuse
+
+        key = tuple(id(f) for f in flatten(self.filters))
+        if self._plan is None or key != self._plan_key:
+            self._plan, self._plan_key = fuse(self.filters), key
+        return self._plan
 
     def forward(self, data: Any) -> Any:
-        for f in self.filters:
+        for f in self.execution_plan():
             data = f.forward(data)
         return data
 

@@ -65,6 +65,20 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Y[r, j] = X[r, cols[j]]: regroup the columns (fields) of a resident batch, e.g. to lay
+// (u, v) / (q, t) partners next to each other.  One warp per row; writes are coalesced,
+// reads stay inside one row (at most a few KB apart).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    gather_cols_kernel(const int* __restrict__ cols, int n_out, const T* __restrict__ X, size_t ldx,
+                       T* __restrict__ Y, size_t ldy, long long n_rows) {
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const T* xr = X + static_cast<size_t>(row) * ldx;
+    T* yr = Y + static_cast<size_t>(row) * ldy;
+    for (int j = threadIdx.x & 31; j < n_out; j += 32) yr[j] = __ldg(xr + __ldg(cols + j));
+}
+
 template <typename T>
 __global__ void compare_mask_kernel(const T* __restrict__ values, size_t stride, long long n,
                                     int op, T thr, uint8_t* __restrict__ mask) {
@@ -146,6 +160,26 @@ extern "C" int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src, 
     if (elem_size == 4)
         return launch_gather<uint32_t>(idx, n_out, n_src, X, ldx, Y, ldy, n_fields, err_flag, st);
     return launch_gather<uint2>(idx, n_out, n_src, X, ldx, Y, ldy, n_fields, err_flag, st);
+}
+
+extern "C" int at_gather_cols(const int32_t* cols, int32_t n_out, int64_t n_rows, const void* X, int64_t ldx,
+                              void* Y, int64_t ldy, int elem_size, void* stream) {
+    AT_REQUIRE(cols != nullptr && X != nullptr && Y != nullptr, "at_gather_cols: null argument");
+    AT_REQUIRE(elem_size == 4 || elem_size == 8, "at_gather_cols: elem_size must be 4 or 8");
+    AT_REQUIRE(n_out >= 0 && n_rows >= 0 && ldy >= n_out, "at_gather_cols: bad shape");
+    if (n_out == 0 || n_rows == 0) return AT_OK;
+    const int64_t blocks = (n_rows + 7) / 8;
+    AT_REQUIRE(blocks < (1ll << 31), "at_gather_cols: too many rows");
+    if (elem_size == 4)
+        gather_cols_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            cols, n_out, static_cast<const float*>(X), static_cast<size_t>(ldx), static_cast<float*>(Y),
+            static_cast<size_t>(ldy), n_rows);
+    else
+        gather_cols_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            cols, n_out, static_cast<const double*>(X), static_cast<size_t>(ldx), static_cast<double*>(Y),
+            static_cast<size_t>(ldy), n_rows);
+    AT_LAUNCH_CHECK("gather_cols_kernel");
+    return AT_OK;
 }
 
 extern "C" int at_compare_mask(const void* values, int dtype, int64_t stride, int64_t n, int op,

@@ -176,6 +176,11 @@ AT_API int at_transpose(const void* src, int64_t rows, int64_t cols, int64_t ld_
 AT_API int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src,
                    const void* X, int64_t ldx, void* Y, int64_t ldy,
                    int64_t n_fields, int elem_size, int32_t* err_flag, void* stream);
+/* Y[r, j] = X[r, cols[j]] for j < n_out: regroup the fields of a resident batch so partner
+ * fields (u with v, q with t — GroupByParam, grouping/__init__.py:93-137) sit in adjacent
+ * columns.  cols: device int32[n_out], every entry < ldx.  elem_size 4 or 8. */
+AT_API int at_gather_cols(const int32_t* cols, int32_t n_out, int64_t n_rows, const void* X, int64_t ldx,
+                   void* Y, int64_t ldy, int elem_size, void* stream);
 /* mask[i] = OP(values[i], threshold) — MaskVariable._compute_mask apply_mask.py:160-163.
  * op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.  values: device f32 / f64 (dtype) with element
  * stride `stride`; a float32 array is compared in float32, as numpy does (NEP 50). */

