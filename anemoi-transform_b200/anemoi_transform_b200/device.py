@@ -350,35 +350,55 @@ class DeviceBatch:
         return int(self.data.shape[0])
 
     @classmethod
-    def from_host_fields(cls, arrays: Sequence[np.ndarray]) -> "DeviceBatch":
-        """Upload F host fields (each [n_points]) and pack them point-major."""
+    def from_host_fields(cls, arrays: Sequence[np.ndarray], chunk: int = 64) -> "DeviceBatch":
+        """Upload F host fields (each [n_points]) and pack them point-major.
+
+        Fields go up in chunks of `chunk`: each array is copied straight from where it lives
+        into a field-major staging buffer on the device (no host-side stacking), and the chunk
+        is transposed into its columns of the batch while the next one uploads."""
         torch = require_cuda()
         n_fields = len(arrays)
         if n_fields == 0:
             raise ValueError("empty batch")
-        n_points = int(np.asarray(arrays[0]).size)
-        dtype = np.result_type(*[np.asarray(a).dtype for a in arrays])
+        views = [np.asarray(a).reshape(-1) for a in arrays]
+        n_points = int(views[0].size)
+        dtype = np.result_type(*[v.dtype for v in views])
         if dtype not in (np.float32, np.float64):
             dtype = np.dtype(np.float64)
-        host = np.empty((n_fields, n_points), dtype=dtype)
-        for i, a in enumerate(arrays):
-            a = np.asarray(a).reshape(-1)
-            if a.size != n_points:
-                raise ValueError(f"field {i} has {a.size} points, expected {n_points}")
-            host[i] = a
-        fm = torch.from_numpy(host).cuda()
+        tdtype = torch.float32 if dtype == np.float32 else torch.float64
+        for i, v in enumerate(views):
+            if v.size != n_points:
+                raise ValueError(f"field {i} has {v.size} points, expected {n_points}")
         ld = round_up(n_fields, 4)
-        pm = torch.zeros((n_points, ld), dtype=fm.dtype, device=fm.device)
-        transpose(fm, out=pm)
+        pm = torch.zeros((n_points, ld), dtype=tdtype, device="cuda")
+        chunk = max(1, min(chunk, n_fields))
+        staging = [torch.empty((chunk, n_points), dtype=tdtype, device="cuda") for _ in range(2)]
+        for k, c0 in enumerate(range(0, n_fields, chunk)):
+            fm = staging[k % 2]
+            nf = min(chunk, n_fields - c0)
+            for j in range(nf):
+                v = views[c0 + j]
+                if v.dtype != dtype or not v.flags.c_contiguous:
+                    v = np.ascontiguousarray(v, dtype=dtype)
+                fm[j].copy_(torch.from_numpy(v), non_blocking=False)
+            call("at_transpose", _ptr(fm), nf, n_points, fm.stride(0), c_void_p(pm.data_ptr() + c0 * pm.element_size()), ld, pm.element_size(), stream_ptr())
         return cls(pm, n_fields)
 
-    def to_host_fields(self) -> np.ndarray:
-        """→ numpy [n_fields, n_points] (field-major); unpacked and downloaded once."""
+    def to_host_fields(self, chunk: int = 256) -> np.ndarray:
+        """→ numpy [n_fields, n_points] (field-major); unpacked and downloaded once, in
+        chunks of `chunk` fields so the device-side staging stays small."""
         if self._host is None:
             torch = _torch()
-            fm = torch.empty((self.n_fields, self.n_points), dtype=self.data.dtype, device=self.data.device)
-            call("at_transpose", _ptr(self.data), self.n_points, self.n_fields, self.data.stride(0), _ptr(fm), fm.stride(0), self.data.element_size(), stream_ptr())
-            self._host = fm.cpu().numpy()
+            np_dtype = np.float32 if self.data.dtype == torch.float32 else np.float64
+            host = np.empty((self.n_fields, self.n_points), dtype=np_dtype)
+            chunk = max(1, min(chunk, self.n_fields))
+            fm = torch.empty((chunk, self.n_points), dtype=self.data.dtype, device=self.data.device)
+            esz = self.data.element_size()
+            for c0 in range(0, self.n_fields, chunk):
+                nf = min(chunk, self.n_fields - c0)
+                call("at_transpose", c_void_p(self.data.data_ptr() + c0 * esz), self.n_points, nf, self.data.stride(0), _ptr(fm), fm.stride(0), esz, stream_ptr())
+                host[c0 : c0 + nf] = fm[:nf].cpu().numpy()
+            self._host = host
         return self._host
 
     def host_column(self, col: int) -> np.ndarray:

@@ -37,6 +37,7 @@ struct KnnLevel {
     uint32_t mask;         // bucket count - 1
     int shift;             // cell coordinate shift (level index); < 0 for the brute-force level
     double cover2;         // (kRingSafety · h_l)²: every source closer than this was scanned
+    double h;              // cell edge h0 · 2^l
 };
 
 struct KnnDev {
@@ -371,11 +372,15 @@ __device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, 
 
 // Full k-NN of one query by one warp.  Lane j < k ends up holding the j-th neighbour.
 // Returns tie bits (valid when want_tie).
+//
+// Only the first `max_levels` levels are tried; `done` tells whether the answer is final
+// (the caller hands unfinished queries to the tree search).
 __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double qy, double qz, int k,
-                                            double ub2, bool want_tie, int lane, double& my_d2,
-                                            long long& my_idx) {
+                                            double ub2, bool want_tie, int lane, int max_levels, bool& done,
+                                            double& my_d2, long long& my_idx) {
     unsigned tie = 0;
-    for (int level = 0; level < d.n_levels; ++level) {
+    done = true;
+    for (int level = 0; level < max_levels; ++level) {
         const KnnLevel& L = d.lv[level];
         const bool last = level == d.n_levels - 1;
         // A level whose ring cannot decide anything (cover radius below the best possible
@@ -409,12 +414,15 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
             return tie;
         }
     }
+    done = false;
     return tie;
 }
 
+constexpr long long kPending = -1;  // idx_out[q*k] of a query the near search left to the tree search
+
 __global__ void __launch_bounds__(256)
     knn_query_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
-                     const double* __restrict__ qz, long long nq, int k, double ub2,
+                     const double* __restrict__ qz, long long nq, int k, double ub2, int near_levels,
                      long long* __restrict__ idx_out, double* __restrict__ dist_out,
                      uint8_t* __restrict__ tie_out) {
     const int lane = threadIdx.x & 31;
@@ -423,12 +431,135 @@ __global__ void __launch_bounds__(256)
         const double x = qx[q], y = qy[q], z = qz[q];
         double d2;
         long long idx;
-        const unsigned tie = knn_one(d, x, y, z, k, ub2, tie_out != nullptr, lane, d2, idx);
+        bool done;
+        const unsigned tie = knn_one(d, x, y, z, k, ub2, tie_out != nullptr, lane, near_levels, done, d2, idx);
+        if (!done) {
+            if (lane == 0) idx_out[q * k] = kPending;
+            continue;
+        }
         if (lane < k) {
             idx_out[q * k + lane] = idx;
             if (dist_out != nullptr) dist_out[q * k + lane] = sqrt(d2);
         }
         if (tie_out != nullptr && lane == 0) tie_out[q] = static_cast<uint8_t>(tie);
+    }
+}
+
+// ---- tree search for the queries the near search could not finish -----------------------
+// The grid levels form an implicit octree (cell c of level l has the 8 children 2c+{0,1} of
+// level l-1; every source lies in cell (0,0,0) of the top level).  One thread per pending
+// query walks it depth first, nearest child first, pruning cells whose box is farther than
+// the current k-th best, and scans a cell's bucket once it holds at most kLeafMax points.
+// Hash collisions can make a bucket hold points of other cells: they are just more (valid)
+// candidates; a point met twice is recognised by its (d², index).  The result is the exact
+// k smallest keys (d², index), the same as the near search.
+constexpr int kLeafMax = 48;
+constexpr int kStackMax = 8 * kMaxLevels;
+
+__device__ __forceinline__ double box_min_d2(const KnnDev& d, double h, int cx, int cy, int cz, double qx, double qy,
+                                             double qz) {
+    const double eps = 1e-8 * h;  // the cell assignment is rounded: widen the box a little
+    const double lx = d.ox + cx * h - eps, ly = d.oy + cy * h - eps, lz = d.oz + cz * h - eps;
+    const double w = h + 2.0 * eps;
+    const double dx = fmax(fmax(lx - qx, qx - (lx + w)), 0.0);
+    const double dy = fmax(fmax(ly - qy, qy - (ly + w)), 0.0);
+    const double dz = fmax(fmax(lz - qz, qz - (lz + w)), 0.0);
+    return (dx * dx + dy * dy + dz * dz) * (1.0 - 1e-10);  // a lower bound despite rounding
+}
+
+__global__ void __launch_bounds__(128)
+    knn_tree_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
+                    const double* __restrict__ qz, long long nq, int k, double ub2,
+                    long long* __restrict__ idx_out, double* __restrict__ dist_out, uint8_t* __restrict__ tie_out) {
+    const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (q >= nq || idx_out[q * k] != kPending) return;
+    const double x = qx[q], y = qy[q], z = qz[q];
+    const int kk = k + (tie_out != nullptr ? 1 : 0);  // one extra to see a tie across the k-th place
+
+    double bd[kMaxK + 1];
+    long long bi[kMaxK + 1];
+    int cnt = 0;
+    unsigned long long stack[kStackMax];
+    int sp = 0;
+    const int root = d.n_levels - 2;  // top grid level; the last level is the brute-force bucket
+    stack[sp++] = static_cast<unsigned long long>(root) << 60;
+
+    while (sp > 0) {
+        const unsigned long long e = stack[--sp];
+        const int level = static_cast<int>(e >> 60);
+        const int cx = static_cast<int>((e >> 40) & 0xfffff), cy = static_cast<int>((e >> 20) & 0xfffff),
+                  cz = static_cast<int>(e & 0xfffff);
+        const KnnLevel& L = d.lv[level];
+        const double worst = cnt == kk ? bd[kk - 1] : INFINITY;
+        const double m = box_min_d2(d, L.h, cx, cy, cz, x, y, z);
+        if (m > worst || m >= ub2) continue;  // pruned since it was pushed
+        const uint32_t b = cell_hash(cx, cy, cz) & L.mask;
+        const int s0 = __ldg(L.start + b), s1 = __ldg(L.start + b + 1);
+        if (s1 == s0) continue;
+        if (level == 0 || s1 - s0 <= kLeafMax) {
+            for (int s = s0; s < s1; ++s) {
+                double px, py, pz;
+                long long idx;
+                load_cand(d, L, level == 0, s, px, py, pz, idx);
+                const double c2 = dist2(x, y, z, px, py, pz);
+                if (!(c2 < ub2)) continue;
+                if (cnt == kk && !key_less(c2, idx, bd[kk - 1], bi[kk - 1])) continue;
+                int pos = cnt < kk ? cnt : kk - 1;  // insertion sort, ascending by (d², index)
+                bool dup = false;
+                while (pos > 0 && !key_less(bd[pos - 1], bi[pos - 1], c2, idx)) {
+                    if (bd[pos - 1] == c2 && bi[pos - 1] == idx) {
+                        dup = true;
+                        break;
+                    }
+                    --pos;
+                }
+                if (dup) continue;
+                const int end = cnt < kk ? cnt : kk - 1;
+                for (int j = end; j > pos; --j) {
+                    bd[j] = bd[j - 1];
+                    bi[j] = bi[j - 1];
+                }
+                bd[pos] = c2;
+                bi[pos] = idx;
+                if (cnt < kk) ++cnt;
+            }
+            continue;
+        }
+        // children of level - 1, farthest pushed first so the nearest is popped first
+        const KnnLevel& C = d.lv[level - 1];
+        double cm[8];
+        int order[8];
+        int n_child = 0;
+        for (int c = 0; c < 8; ++c) {
+            const double mc = box_min_d2(d, C.h, 2 * cx + (c & 1), 2 * cy + ((c >> 1) & 1), 2 * cz + (c >> 2), x, y, z);
+            if (mc > worst || mc >= ub2) continue;
+            int p = n_child++;
+            while (p > 0 && cm[order[p - 1]] < mc) {
+                order[p] = order[p - 1];
+                --p;
+            }
+            order[p] = c;
+            cm[c] = mc;
+        }
+        for (int j = 0; j < n_child && sp < kStackMax; ++j) {
+            const int c = order[j];
+            stack[sp++] = (static_cast<unsigned long long>(level - 1) << 60) |
+                          (static_cast<unsigned long long>(2 * cx + (c & 1)) << 40) |
+                          (static_cast<unsigned long long>(2 * cy + ((c >> 1) & 1)) << 20) |
+                          static_cast<unsigned long long>(2 * cz + (c >> 2));
+        }
+    }
+
+    unsigned tie = 0;
+    for (int j = 0; j < k; ++j) {
+        const bool have = j < cnt;
+        idx_out[q * k + j] = have ? bi[j] : d.n;
+        if (dist_out != nullptr) dist_out[q * k + j] = have ? sqrt(bd[j]) : INFINITY;
+        if (have && j > 0 && bd[j] == bd[j - 1]) tie |= 1u;
+    }
+    if (tie_out != nullptr) {
+        if (cnt > k && bd[k] == bd[k - 1]) tie |= 2u;
+        tie_out[q] = static_cast<uint8_t>(tie);
     }
 }
 
@@ -441,7 +572,8 @@ __global__ void __launch_bounds__(256)
     for (long long q = first + ((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5); q < end; q += warps) {
         double d2;
         long long idx;
-        knn_one(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d2, idx);
+        bool done;
+        knn_one(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d.n_levels, done, d2, idx);
         const double second = __shfl_sync(0xffffffffu, d2, 1);
         best = fmin(best, second);
     }
@@ -662,7 +794,8 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         L.perm = d_perm;
         L.mask = m - 1;
         L.shift = l;
-        const double cover = kRingSafety * k->h0 * std::ldexp(1.0, l);
+        L.h = k->h0 * std::ldexp(1.0, l);
+        const double cover = kRingSafety * L.h;
         L.cover2 = cover * cover;
     }
     {
@@ -672,6 +805,7 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         L.mask = 0;
         L.shift = -1;
         L.cover2 = INFINITY;
+        L.h = INFINITY;
     }
     k->dev.x = k->d_x;
     k->dev.y = k->d_y;
@@ -703,9 +837,18 @@ extern "C" int at_knn_query(const at_knn_t* k, const double* qx, const double* q
     AT_REQUIRE(!(upper_bound != upper_bound) && upper_bound >= 0, "at_knn_query: bad distance_upper_bound");
     if (nq == 0) return AT_OK;
     const double ub2 = upper_bound * upper_bound;
+    // near search: ring 1 of the two finest levels, one warp per query; whatever it cannot
+    // decide (queries far from every source) goes to the per-thread tree search
+    const int n_grid = k->dev.n_levels - 1;
+    const int near_levels = std::min(2, n_grid);
     knn_query_kernel<<<query_blocks(nq), 256, 0, as_stream(stream)>>>(
-        k->dev, qx, qy, qz, nq, kk, ub2, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+        k->dev, qx, qy, qz, nq, kk, ub2, near_levels, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
     AT_LAUNCH_CHECK("knn_query_kernel");
+    const long long tree_blocks = (nq + 127) / 128;
+    AT_REQUIRE(tree_blocks < (1ll << 31), "at_knn_query: too many queries");
+    knn_tree_kernel<<<static_cast<unsigned>(tree_blocks), 128, 0, as_stream(stream)>>>(
+        k->dev, qx, qy, qz, nq, kk, ub2, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+    AT_LAUNCH_CHECK("knn_tree_kernel");
     return AT_OK;
 }
 

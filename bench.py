@@ -111,6 +111,30 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank: int):
+    """Run this rank (and allocate its pinned buffers) on the NUMA node its GPU hangs off, so
+    H2D / D2H DMA does not cross the inter-socket link.  Best effort: sysfs may be hidden."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return node
+    except Exception as e:
+        log("NUMA binding skipped:", e)
+    return None
+
+
 def cpu_baseline(w, steps: int = 3) -> dict:
     """The oracle's C port of the reference's per-field csr_matvec loop, all host threads."""
     from oracle import spmm as ospmm
@@ -201,6 +225,7 @@ def run_gpu(args):
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     _cabi.load(check_device=True)  # fail loudly if the CUDA library or the device is missing
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -355,6 +380,7 @@ def run_gpu(args):
         "parity_spot_check": e2e_parity,
         "gpu_launches_per_step": 3 * chunks,
         "host_pool_fields": pool,
+        "numa_node": numa_node,
     }
     pipe.close()
 
