@@ -316,7 +316,8 @@ def test_pipeline_fusion_one_launch_same_result(F, golden_regrid, tmp_path):
     fused = pipe.forward(None)
     assert plan[1].last_forward_was_fused
     _same_fieldlists(fused, _run_unfused(filters, src.forward(None)))
-    assert [f.metadata("param") for f in fused] == ["z_land", "ws_land", "wdir", "ws_land", "wdir", "ws_land", "wdir", "q", "t", "r_land", "t", "q", "r_land"] or True
+    params = [f.metadata("param") for f in fused]
+    assert "lsm" not in params and params.count("ws_land") == 3 and params.count("r_land") == 2 and params[0] == "z_land"
     # return_inputs="none", reversed filters and a file mask fuse as well
     np.save(tmp_path / "mask.npy", (np.random.default_rng(1).uniform(size=golden_regrid["t_lat"].size) < 0.2).astype(np.float32))
     filters = [F("regrid", matrix=matrix), F("q_to_r", return_inputs="none"), F("uv_to_ddff"), F("apply_mask", path=str(tmp_path / "mask.npy"), mask_value=1)]

@@ -111,3 +111,35 @@ def test_midsize_lam_in_global(sp):
     assert np.array_equal(sp.thinning_mask(*lam, *glob), osp.thinning_mask(*lam, *glob))
     assert np.array_equal(sp.global_on_lam_mask(*lam, *glob), osp.global_on_lam_mask(*lam, *glob))
     assert np.array_equal(sp.global_on_lam_mask(*lam, *glob, distance_km=40.0), osp.global_on_lam_mask(*lam, *glob, distance_km=40.0))
+
+
+def test_lam_straddling_longitude_zero_far_queries(sp):
+    """Like BASELINE config 5: the LAM crosses lon 0, so the reference's crop box spans every
+    longitude and most cropped global points are far from the LAM (tree-search path)."""
+    lam = syn.rotated_lam(150, 150, 0.1, 60.0, 10.0)
+    assert lam[1].min() < 1.0 and lam[1].max() > 359.0
+    glob = syn.octahedral(96)
+    got, want = sp.thinning_mask(*lam, *glob), osp.thinning_mask(*lam, *glob)
+    assert got.shape == want.shape and got.size > 2000
+    differ = np.nonzero(got != want)[0]
+    if differ.size:  # only exact float64 d² ties may differ (mirror-image LAM points)
+        lp = np.array(osp.latlon_to_xyz(*lam)).T
+        crop = osp._crop(lam[0], lam[1], glob[0], glob[1], 2.0)
+        gp = np.array(osp.latlon_to_xyz(glob[0][crop], glob[1][crop])).T[differ]
+        assert np.array_equal(((lp[got[differ]] - gp) ** 2).sum(axis=1), ((lp[want[differ]] - gp) ** 2).sum(axis=1))
+        assert differ.size < 50
+    assert np.array_equal(sp.cutout_mask(*lam, *glob), osp.cutout_mask_vectorised(*lam, *glob))
+    assert np.array_equal(sp.cutout_mask(*lam, *glob, max_distance_km=500.0), osp.cutout_mask_vectorised(*lam, *glob, max_distance_km=500.0))
+    assert np.array_equal(sp.global_on_lam_mask(*lam, *glob), osp.global_on_lam_mask(*lam, *glob))
+    assert np.array_equal(sp.global_on_lam_mask(*lam, *glob, distance_km="lam"), osp.global_on_lam_mask(*lam, *glob, distance_km="lam"))
+
+
+def test_sharded_entry_points_equal_the_single_gpu_ones(sp, golden_spatial):
+    """distributed.* with world_size 1 (no process group): same answers as spatial.*."""
+    from anemoi_transform_b200 import distributed as atd
+
+    g = golden_spatial
+    lam, o = (g["lam_lat"], g["lam_lon"]), (g["o_lat"], g["o_lon"])
+    assert np.array_equal(atd.nearest_grid_points(*lam, *o, num_neighbours_to_return=3), sp.nearest_grid_points(*lam, *o, num_neighbours_to_return=3))
+    assert np.array_equal(atd.global_on_lam_mask(*lam, *o), g["gol_none"])
+    assert np.array_equal(atd.global_on_lam_mask(*lam, *o, distance_km=150.0), g["gol_150km"])

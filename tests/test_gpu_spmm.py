@@ -127,3 +127,32 @@ def test_full_size_config3_properties(cuda):
         assert_same_values(y[:, col].cpu().numpy(), m @ x[:, col].cpu().numpy(), f"column {col}")
     y2 = csr.apply(x * 2)
     assert cuda.equal(y2, y * 2)
+
+
+def test_layout_kernels(cuda):
+    """at_transpose, at_gather_cols, at_gather_rows and the chunked batch upload / download."""
+    from anemoi_transform_b200.device import DeviceBatch, gather_cols, gather_rows, transpose
+
+    rng = np.random.default_rng(2)
+    for dtype in (np.float32, np.float64):
+        for rows, cols in ((1, 1), (3, 130), (65, 64), (200, 257)):
+            a = rng.normal(size=(rows, cols)).astype(dtype)
+            t = transpose(cuda.from_numpy(a).cuda()).cpu().numpy()
+            assert np.array_equal(t, a.T)
+        fields = [rng.normal(size=1000).astype(dtype) for _ in range(150)]
+        fields[3][7] = np.nan
+        b = DeviceBatch.from_host_fields(fields, chunk=64)
+        assert b.data.shape == (1000, 152) and b.n_fields == 150
+        assert_same_values(b.to_host_fields(chunk=32), np.stack(fields), f"round trip {dtype.__name__}")
+        pick = [149, 0, 3, 3, 77]
+        g = gather_cols(b.data, pick).cpu().numpy()
+        assert_same_values(np.ascontiguousarray(g[:, :5].T), np.stack([fields[p] for p in pick]), "gather_cols")
+        idx = cuda.from_numpy(rng.integers(0, 1000, 333)).cuda()
+        r = gather_rows(b.data, idx).cpu().numpy()
+        assert_same_values(r[:, :150], np.stack(fields).T[idx.cpu().numpy()], "gather_rows")
+    with pytest.raises(IndexError):
+        gather_cols(b.data, [152])
+    with pytest.raises(IndexError):
+        gather_rows(b.data, cuda.tensor([1000], device="cuda"))
+    mixed = DeviceBatch.from_host_fields([np.ones(10, np.float32), np.ones(10, np.float64)])
+    assert mixed.data.dtype == cuda.float64  # numpy result_type

@@ -235,5 +235,3 @@ def test_product_never_imports_the_oracle():
     for path in (REPO / "anemoi-transform_b200").rglob("*.py"):
         text = path.read_text()
         assert "import oracle" not in text and "from oracle" not in text, path
-    for path in (REPO / "anemoi-transform_b200" / "csrc").glob("*"):
-        assert "oracle/" not in path.read_text() or path.name.endswith(".cuh") or True
