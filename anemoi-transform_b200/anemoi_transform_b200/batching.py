@@ -10,12 +10,13 @@ from .device import DeviceBatch, gather_cols, require_cuda, round_up
 from .fields import device_column_of
 
 
-def fields_to_batch(fields: Sequence[Any]) -> DeviceBatch:
+def fields_to_batch(fields: Sequence[Any], host_values: Sequence[Any] | None = None) -> DeviceBatch:
     """A point-major batch whose column j holds the values of fields[j].
 
     Fields already resident in HBM (outputs of an earlier filter of this package) are not
     round-tripped through the host: consecutive columns of one batch are used in place,
-    other arrangements are re-packed on the device.
+    other arrangements are re-packed on the device.  `host_values[j]`, when given, is
+    fields[j].to_numpy(flatten=True) already fetched by the caller.
     """
     torch = require_cuda()
     cols = [device_column_of(f) for f in fields]
@@ -44,7 +45,9 @@ def fields_to_batch(fields: Sequence[Any]) -> DeviceBatch:
                     for k, (j, _) in enumerate(pairs):
                         out[:, j] = tmp[:, k]
             return DeviceBatch(out, n)
-    return DeviceBatch.from_host_fields([f.to_numpy(flatten=True) for f in fields])
+    if host_values is not None and all(v is not None for v in host_values):
+        return DeviceBatch.from_host_fields(list(host_values))
+    return DeviceBatch.from_host_fields([np.asarray(f.to_numpy()).reshape(-1) for f in fields])
 
 
 def numpy_dtype_of(batch: DeviceBatch):

@@ -337,32 +337,126 @@ def compare_mask(values, op: int, threshold: float):
     return mask
 
 
+_STAGING_BYTES = 128 << 20  # per slot; two slots pinned + two on the device, allocated once
+_COPY_THREADS = None
+_N_COPY_THREADS = 1
+_RING = None
+
+
+def _chunk_fields(n_fields: int, field_bytes: int, chunk: int | None) -> int:
+    if chunk is None:
+        chunk = max(1, min(256, _STAGING_BYTES // max(1, field_bytes)))
+    return max(1, min(int(chunk), n_fields))
+
+
+def _parallel_copy(pairs) -> None:
+    """dst[...] = src for (dst, src) numpy pairs; big batches are spread over host threads
+    (numpy releases the GIL while it copies).  One task per thread, not per field: a pool task
+    costs tens of microseconds, a 260 KB field copies in about as long."""
+    global _COPY_THREADS, _N_COPY_THREADS
+    total = sum(d.nbytes for d, _ in pairs)
+    if total < (4 << 20):
+        for d, s in pairs:
+            np.copyto(d, s, casting="unsafe")
+        return
+    if _COPY_THREADS is None:
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        _N_COPY_THREADS = max(1, min(8, (len(os.sched_getaffinity(0)) or 2) - 1))
+        _COPY_THREADS = ThreadPoolExecutor(max_workers=_N_COPY_THREADS, thread_name_prefix="at-copy")
+    if len(pairs) < _N_COPY_THREADS:  # few large fields: split them
+        parts = -(-_N_COPY_THREADS // len(pairs))
+        split = []
+        for d, s in pairs:
+            cuts = np.linspace(0, d.size, parts + 1).astype(np.int64)
+            split += [(d[a:b], s[a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        pairs = split
+    n_groups = min(_N_COPY_THREADS, len(pairs))
+    groups = [pairs[g::n_groups] for g in range(n_groups)]
+
+    def work(group):
+        for d, s in group:
+            np.copyto(d, s, casting="unsafe")
+
+    futures = [_COPY_THREADS.submit(work, g) for g in groups[1:]]
+    work(groups[0])  # the calling thread takes a share
+    for f in futures:
+        f.result()
+
+
+class _StagingRing:
+    """Two pinned host slots and two device slots of raw bytes, reused by every upload /
+    download of the process (pinning memory is slow; do it once)."""
+
+    def __init__(self, nbytes: int):
+        torch = _torch()
+        self.nbytes = nbytes
+        self.pinned = [torch.empty((nbytes,), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.device = [torch.empty((nbytes,), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        self.events = [None, None]
+        self.busy = False
+
+    def wait(self, slot: int) -> None:
+        if self.events[slot] is not None:
+            self.events[slot].synchronize()
+            self.events[slot] = None
+
+    def record(self, slot: int) -> None:
+        torch = _torch()
+        ev = torch.cuda.Event()
+        ev.record()
+        self.events[slot] = ev
+
+    def release(self) -> None:
+        self.wait(0)
+        self.wait(1)
+        self.busy = False
+
+
+def _staging_ring(nbytes: int) -> _StagingRing:
+    """The process-wide ring, grown when a chunk needs more (per device, single-threaded use)."""
+    global _RING
+    torch = _torch()
+    nbytes = round_up(max(nbytes, 1 << 20), 1 << 20)
+    dev = torch.cuda.current_device()
+    if _RING is None or _RING.nbytes < nbytes or _RING.device[0].device.index != dev or _RING.busy:
+        ring = _StagingRing(nbytes)
+        if _RING is None or not _RING.busy:
+            _RING = ring
+    else:
+        ring = _RING
+    ring.busy = True
+    return ring
+
+
 class DeviceBatch:
     """A batch of fields resident in HBM, point-major: data[n_points, ld], ld % 4 == 0."""
 
     def __init__(self, data, n_fields: int):
         self.data = data
         self.n_fields = int(n_fields)
-        self._host = None  # lazily unpacked field-major copy, shared by the batch's fields
+        self._host = None  # per-column host arrays downloaded at the first to_numpy(), handed out once
 
     @property
     def n_points(self) -> int:
         return int(self.data.shape[0])
 
     @classmethod
-    def from_host_fields(cls, arrays: Sequence[np.ndarray], chunk: int = 64) -> "DeviceBatch":
+    def from_host_fields(cls, arrays: Sequence[np.ndarray], chunk: int | None = None) -> "DeviceBatch":
         """Upload F host fields (each [n_points]) and pack them point-major.
 
-        Fields go up in chunks of `chunk`: each array is copied straight from where it lives
-        into a field-major staging buffer on the device (no host-side stacking), and the chunk
-        is transposed into its columns of the batch while the next one uploads."""
+        Fields go up in chunks: host threads copy a chunk's arrays from wherever they live
+        (pageable memory as a rule) into a pinned staging slot, one async H2D moves the slot
+        into a field-major device buffer, `at_transpose` writes it into its columns of the
+        batch.  Two slots, so the host copies of chunk k+1 overlap the DMA of chunk k."""
         torch = require_cuda()
         n_fields = len(arrays)
         if n_fields == 0:
             raise ValueError("empty batch")
         views = [np.asarray(a).reshape(-1) for a in arrays]
         n_points = int(views[0].size)
-        dtype = np.result_type(*[v.dtype for v in views])
+        dtype = np.result_type(*{v.dtype for v in views})
         if dtype not in (np.float32, np.float64):
             dtype = np.dtype(np.float64)
         tdtype = torch.float32 if dtype == np.float32 else torch.float64
@@ -371,38 +465,85 @@ class DeviceBatch:
                 raise ValueError(f"field {i} has {v.size} points, expected {n_points}")
         ld = round_up(n_fields, 4)
         pm = torch.zeros((n_points, ld), dtype=tdtype, device="cuda")
-        chunk = max(1, min(chunk, n_fields))
-        staging = [torch.empty((chunk, n_points), dtype=tdtype, device="cuda") for _ in range(2)]
-        for k, c0 in enumerate(range(0, n_fields, chunk)):
-            fm = staging[k % 2]
-            nf = min(chunk, n_fields - c0)
-            for j in range(nf):
-                v = views[c0 + j]
-                if v.dtype != dtype or not v.flags.c_contiguous:
-                    v = np.ascontiguousarray(v, dtype=dtype)
-                fm[j].copy_(torch.from_numpy(v), non_blocking=False)
-            call("at_transpose", _ptr(fm), nf, n_points, fm.stride(0), c_void_p(pm.data_ptr() + c0 * pm.element_size()), ld, pm.element_size(), stream_ptr())
+        chunk = _chunk_fields(n_fields, n_points * dtype.itemsize, chunk)
+        ring = _staging_ring(chunk * n_points * dtype.itemsize)
+        pins = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.pinned]
+        devs = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.device]
+        try:
+            for k, c0 in enumerate(range(0, n_fields, chunk)):
+                slot = k % 2
+                nf = min(chunk, n_fields - c0)
+                ring.wait(slot)  # the DMA that last read this pinned slot
+                _parallel_copy([(pins[slot][j].numpy(), views[c0 + j]) for j in range(nf)])
+                devs[slot][:nf].copy_(pins[slot][:nf], non_blocking=True)
+                ring.record(slot)
+                call("at_transpose", _ptr(devs[slot]), nf, n_points, n_points, c_void_p(pm.data_ptr() + c0 * pm.element_size()), ld, pm.element_size(), stream_ptr())
+        finally:
+            ring.release()
         return cls(pm, n_fields)
 
-    def to_host_fields(self, chunk: int = 256) -> np.ndarray:
-        """→ numpy [n_fields, n_points] (field-major); unpacked and downloaded once, in
-        chunks of `chunk` fields so the device-side staging stays small."""
+    def _download(self, dests: Sequence[np.ndarray], first_col: int = 0, chunk: int | None = None) -> None:
+        """dests[j][:] = column first_col + j: chunks are transposed field-major on the device,
+        moved into a pinned slot by one async D2H, and copied into the destinations by host
+        threads while the next chunk is in flight."""
+        torch = _torch()
+        tdtype = self.data.dtype
+        n_points, esz, n = self.n_points, self.data.element_size(), len(dests)
+        chunk = _chunk_fields(n, n_points * esz, chunk)
+        ring = _staging_ring(chunk * n_points * esz)
+        pins = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.pinned]
+        devs = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.device]
+        pending = None
+
+        def drain(p):
+            slot, c0, nf = p
+            ring.wait(slot)
+            _parallel_copy([(dests[c0 + j], pins[slot][j].numpy()) for j in range(nf)])
+
+        try:
+            for k, c0 in enumerate(range(0, n, chunk)):
+                slot = k % 2
+                nf = min(chunk, n - c0)
+                call("at_transpose", c_void_p(self.data.data_ptr() + (first_col + c0) * esz), n_points, nf, self.data.stride(0), _ptr(devs[slot]), n_points, esz, stream_ptr())
+                pins[slot][:nf].copy_(devs[slot][:nf], non_blocking=True)
+                ring.record(slot)
+                if pending is not None:
+                    drain(pending)
+                pending = (slot, c0, nf)
+            if pending is not None:
+                drain(pending)
+        finally:
+            ring.release()
+
+    def _np_dtype(self):
+        return np.dtype(np.float32 if self.data.dtype == _torch().float32 else np.float64)
+
+    def to_host_fields(self, chunk: int | None = None) -> np.ndarray:
+        """→ numpy [n_fields, n_points] (field-major), a fresh array."""
+        host = np.empty((self.n_fields, self.n_points), dtype=self._np_dtype())
+        self._download([host[j] for j in range(self.n_fields)], 0, chunk)
+        return host
+
+    def take_column(self, col: int) -> np.ndarray:
+        """A fresh host array with the values of column `col`, owned by the caller.
+
+        The first request downloads every column of the batch (one pass, one array per field);
+        each array is handed out once without a further copy.  A column asked for again is
+        downloaded again (the device copy is the source of truth — callers may mutate what
+        they were given, e.g. apply_mask.py:184-185)."""
         if self._host is None:
-            torch = _torch()
-            np_dtype = np.float32 if self.data.dtype == torch.float32 else np.float64
-            host = np.empty((self.n_fields, self.n_points), dtype=np_dtype)
-            chunk = max(1, min(chunk, self.n_fields))
-            fm = torch.empty((chunk, self.n_points), dtype=self.data.dtype, device=self.data.device)
-            esz = self.data.element_size()
-            for c0 in range(0, self.n_fields, chunk):
-                nf = min(chunk, self.n_fields - c0)
-                call("at_transpose", c_void_p(self.data.data_ptr() + c0 * esz), self.n_points, nf, self.data.stride(0), _ptr(fm), fm.stride(0), esz, stream_ptr())
-                host[c0 : c0 + nf] = fm[:nf].cpu().numpy()
-            self._host = host
-        return self._host
+            self._host = [np.empty((self.n_points,), dtype=self._np_dtype()) for _ in range(self.n_fields)]
+            self._download(self._host)
+        arr = self._host[col]
+        if arr is None:
+            arr = np.empty((self.n_points,), dtype=self._np_dtype())
+            self._download([arr], first_col=col)
+        else:
+            self._host[col] = None
+        return arr
 
     def host_column(self, col: int) -> np.ndarray:
-        return self.to_host_fields()[col]
+        return self.take_column(col)
 
 
 class HostPipeline:

@@ -112,7 +112,7 @@ class DeviceColumnField(WrappedField):
 
     def to_numpy(self, flatten: bool = False, dtype: type | None = None, index: Any | None = None) -> np.ndarray:
         # each call hands out a fresh array (reference NewDataField.to_numpy(flatten=True) copies)
-        data = self._batch.host_column(self._col).copy()
+        data = self._batch.take_column(self._col)
         if dtype is not None:
             data = data.astype(dtype)
         if not flatten:

@@ -95,13 +95,24 @@ class _BatchedInterpolator:
 
     def regrid_batch(self, fields: list[Any]) -> list[Any]:
         self.prepare(fields[0])
-        # numpy dtypes differ per field in principle; batch runs of equal dtype together
+        # numpy dtypes differ per field in principle; batch runs of equal dtype together.
+        # Host values are fetched once here (to_numpy decodes / copies) and handed to the upload.
+        from ...fields import device_column_of
+
         out: list[Any] = [None] * len(fields)
         by_dtype: dict[Any, list[int]] = {}
+        host_values: dict[int, np.ndarray] = {}
         for i, f in enumerate(fields):
-            by_dtype.setdefault(_value_dtype(f), []).append(i)
+            col = device_column_of(f)
+            if col is not None:
+                key = str(col[0].data.dtype)
+            else:
+                # reshape(-1) instead of flatten=True: no host copy when the field is contiguous
+                host_values[i] = v = np.asarray(f.to_numpy()).reshape(-1)
+                key = "torch.float32" if v.dtype == np.float32 else "torch.float64"
+            by_dtype.setdefault(key, []).append(i)
         for _, idxs in by_dtype.items():
-            batch = fields_to_batch([fields[i] for i in idxs])
+            batch = fields_to_batch([fields[i] for i in idxs], host_values=[host_values.get(i) for i in idxs])
             result = self.apply(batch)
             lat, lon = self.output_grid(fields[idxs[0]])
             for j, i in enumerate(idxs):
@@ -118,16 +129,6 @@ class _BatchedInterpolator:
 
     def output_grid(self, field: Any):
         raise NotImplementedError
-
-
-def _value_dtype(field: Any):
-    from ...fields import device_column_of
-
-    col = device_column_of(field)
-    if col is not None:
-        return str(col[0].data.dtype)
-    dt = np.asarray(field.to_numpy(flatten=True)).dtype if not hasattr(field, "_b200_dtype") else field._b200_dtype
-    return "torch.float32" if dt == np.float32 else "torch.float64"
 
 
 class MIRMatrix(_BatchedInterpolator):

@@ -80,6 +80,30 @@ def config1(tmp):
             "gpu_fields_per_s": 64 / gpu_s, "cpu_ref_fields_per_s_1thread": 64 / cpu_s, "bit_exact": same(out, ref)}
 
 
+def config3_dropin(tmp):
+    """Config 3's grids through the drop-in filter API with ordinary (pageable) numpy fields:
+    FieldList in -> FieldList out -> to_numpy of every field, 512 fields per call."""
+    s_lat, s_lon = syn.regular_latlon(0.25)
+    t_lat, t_lon = syn.n320_like()
+    d, i, p, shape = syn.bilinear_matrix(0.25, t_lat, t_lon)
+    syn.save_regrid_npz(tmp / "c3.npz", d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    n = 512
+    rng = np.random.default_rng(0)
+    fields = [rng.standard_normal(shape[1], dtype=np.float32) for _ in range(n)]
+    fl = ekd.from_source("list-of-dicts", [dict(param="t", levelist=s, values=v, latitudes=s_lat, longitudes=s_lon) for s, v in enumerate(fields)])
+    flt = create_filter_by_name("regrid", matrix=str(tmp / "c3.npz"))
+
+    def run():
+        return [f.to_numpy(flatten=True) for f in flt.forward(fl)]
+
+    gpu_s, out = wall(run)
+    m = csr_array((d, i, p), shape=shape)
+    cpu_s, ref = wall(lambda: [m @ f for f in fields[:32]], repeat=1)
+    return {"config": "3 (drop-in): regrid filter 0.25deg -> N320-shaped, 512 pageable float32 fields, FieldList in -> to_numpy of every output",
+            "gpu_fields_per_s": n / gpu_s, "gpu_s": gpu_s, "host_GBps_in_plus_out": 4 * n * (shape[0] + shape[1]) / gpu_s / 1e9,
+            "cpu_ref_fields_per_s_1thread": 32 / cpu_s, "bit_exact_32_fields": all(same(a, b) for a, b in zip(out[:32], ref))}
+
+
 def config2():
     src, tgt = syn.regular_latlon(0.25), syn.n320_like()
     gpu_s, (idx, dist, ties) = wall(lambda: spatial.nearest_grid_points(*src, *tgt, _return_ties=True))
@@ -137,6 +161,34 @@ def config4():
             "fused_equals_unfused_bitwise": same(fused_host, unfused_host), "n_src_referenced": nref}
 
 
+def config3_f64():
+    """Config 3's matrix in the dtypes the operational chain produces: MIR writes float64 weights,
+    GRIB decodes to float64 values; numpy promotes the mixed cases to float64 results."""
+    t_lat, t_lon = syn.n320_like()
+    d, i, p, shape = syn.bilinear_matrix(0.25, t_lat, t_lon)
+    nref = int(np.unique(i).size)
+    m64 = csr_array((d.astype(np.float64), i, p), shape=shape)
+    out = {"config": "3 (dtype variants): regrid 0.25deg -> N320-shaped, 4-nnz bilinear, float64 results, kernel-only", "n_src_referenced": nref}
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for wname, wdt, xname, xdt, F in (("f64", np.float64, "f64", torch.float64, 1560), ("f64", np.float64, "f32", torch.float32, 1560), ("f32", np.float32, "f64", torch.float64, 1560)):
+        csr = CsrMatrix(d.astype(wdt), i, p, shape)
+        X = torch.randn((shape[1], F), device="cuda", dtype=xdt, generator=gen) * 15 + 280
+        Y = torch.empty((shape[0], F), device="cuda", dtype=torch.float64)
+        xs, ws = X.element_size(), np.dtype(wdt).itemsize
+        alg = xs * F * nref + 8 * F * shape[0] + (4 + ws) * d.size + 4 * (shape[0] + 1)
+        wide = dev_ms(lambda: csr.apply(X, out=Y))
+        y_wide = Y[:, :: F // 3].cpu().numpy()
+        scalar = dev_ms(lambda: csr.apply(X, out=Y, variant=0x200), n=3, warm=1)
+        y_scalar = Y[:, :: F // 3].cpu().numpy()
+        mm = m64 if wdt == np.float64 else csr_array((d, i, p), shape=shape)
+        ref = np.stack([mm @ X[:, c].cpu().numpy() for c in range(0, F, F // 3)], axis=1)
+        out[f"matrix_{wname}_fields_{xname}"] = {"fields": F, "ms": wide, "fields_per_s": F / (wide * 1e-3), "algorithmic_GBps": alg / wide / 1e6,
+                                               "scalar_column_kernel_ms": scalar, "bit_exact_sampled_columns": same(y_wide, ref) and same(y_scalar, ref)}
+        del csr, X, Y
+        torch.cuda.empty_cache()
+    return out
+
+
 def config5():
     lam = syn.rotated_lam(1000, 1000, 0.018, 60.0, 10.0)
     glob = syn.octahedral(1280)
@@ -166,12 +218,12 @@ def main():
 
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/configs.json")
-    ap.add_argument("--only", default="1,2,4,5")
+    ap.add_argument("--only", default="1,2,3d,3f64,4,5")
     a = ap.parse_args()
     _cabi.load(check_device=True)
     results = {"host_cpus": os.cpu_count(), "gpu": torch.cuda.get_device_name(0)}
     with tempfile.TemporaryDirectory() as tmp:
-        for key, fn in (("1", lambda: config1(Path(tmp))), ("2", config2), ("4", config4), ("5", config5)):
+        for key, fn in (("1", lambda: config1(Path(tmp))), ("2", config2), ("3d", lambda: config3_dropin(Path(tmp))), ("3f64", config3_f64), ("4", config4), ("5", config5)):
             if key in a.only.split(","):
                 t0 = time.perf_counter()
                 results[f"config{key}"] = fn()

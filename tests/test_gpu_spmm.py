@@ -88,6 +88,40 @@ def test_irregular_float32_matrix_general_kernel(cuda):
     assert_same_values(np.stack([ospmm.csr_matvec_sequential(ptr, idx, dat, x) for x in fields]), want, "oracle restatement")
 
 
+@pytest.mark.parametrize("wdt,xdt", [(np.float64, np.float64), (np.float64, np.float32), (np.float32, np.float64)])
+def test_float64_results_vectorised_and_scalar_kernels(cuda, wdt, xdt):
+    """float64 matrix and / or float64 fields (MIR weights are float64, GRIB values decode to
+    float64): spmm_f64_kernel (4-field groups) and the scalar-column kernel (variant bit 9)
+    against scipy, on the regular config-1 matrix and on an irregular one whose row 7 spills
+    the staged segment (global-memory path), for ragged field counts."""
+    from anemoi_transform_b200.device import CsrMatrix
+
+    rng = np.random.default_rng(11)
+    t_lat, t_lon = syn.octahedral(48)
+    d, i, p, shape = syn.bilinear_matrix(1.0, t_lat, t_lon)
+    n_t, n_s = 1500, 4000
+    lens = rng.integers(0, 41, n_t)
+    lens[7], lens[8] = 3000, 0
+    ptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    idx = rng.integers(0, n_s, ptr[-1]).astype(np.int32)
+    dat = rng.normal(size=ptr[-1])
+    dat[rng.uniform(size=dat.size) < 0.05] = 0.0
+    for name, (md, mi, mp, mshape) in {"bilinear": (d, i, p, shape), "irregular": (dat, idx, ptr, (n_t, n_s))}.items():
+        md = md.astype(wdt)
+        m = csr_array((md, mi, mp), shape=mshape)
+        csr = CsrMatrix(md, mi, mp, mshape)
+        for n_fields in (1, 3, 4, 37, 129, 260):
+            fields = (rng.normal(size=(n_fields, mshape[1])) * 10 + 280).astype(xdt)
+            fields[0, 17] = np.nan
+            fields[n_fields // 2, 100] = np.inf
+            want = np.stack([m @ x for x in fields])
+            assert want.dtype == np.float64
+            for variant in (0, 1, 4, 0x1000, 0x200):
+                got = _apply(cuda, csr, fields, variant)
+                assert got.dtype == np.float64
+                assert_same_values(got, want, f"{name} {wdt.__name__}@{xdt.__name__} F={n_fields} variant {variant:#x}")
+
+
 def test_empty_and_degenerate(cuda):
     from anemoi_transform_b200.device import CsrMatrix
 
