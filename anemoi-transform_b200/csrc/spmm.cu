@@ -325,6 +325,7 @@ struct PointwiseArgs {
     size_t ldx, ldy;
     long long n_rows;
     int rows_per_cta;
+    int n_tiles;
 };
 
 __device__ __forceinline__ void load4(const float* p, float& a, float& b, float& c, float& d) {
@@ -337,30 +338,66 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
     a = v0.x, b = v0.y, c = v1.x, d = v1.y;
 }
 
+// Warp w of a CTA owns tile-table entry blockIdx.y * 8 + w (32 lanes x 4 input columns, one
+// kind) for all of the CTA's rows: the 8 warps together read 4 KB of contiguous columns per row
+// (DRAM page locality), and everything row-invariant (pressures, clip bounds, mask bits) lives
+// in registers.  Copy-like tiles (clip / mask only) are latency-bound: kPwRows rows of loads in
+// flight.  Transcendental tiles are issue-bound (uv_to_ddff is ~85 instructions per pair against
+// ~88 issue slots per 16 bytes at the HBM roofline): one copy of the epilogue code, the next
+// row's load in flight behind it, 4 CTAs per SM.
+constexpr int kPwRows = 4;
+
 template <typename T>
-__global__ void __launch_bounds__(kThreads) pointwise_kernel(const PointwiseArgs<T> f) {
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_kernel(const PointwiseArgs<T> f) {
     const long long r0 = static_cast<long long>(blockIdx.x) * f.rows_per_cta;
     const int nrows = static_cast<int>(min(static_cast<long long>(f.rows_per_cta), f.n_rows - r0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const EpiTile tile = f.tiles[blockIdx.y];
-    if (lane >= tile.n_vec || warp >= nrows) return;
-    const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
+    const int t_index = blockIdx.y * kWarps + warp;
+    if (t_index >= f.n_tiles) return;
+    const EpiTile tile = f.tiles[t_index];
+    if (lane >= tile.n_vec) return;
     const bool any_mask = f.row_mask != nullptr && (tile.flags_any & AT_COL_MASK) != 0;
     const T* xcol = f.X + 4 * static_cast<size_t>(tile.in_vec0 + lane);
-    // The next row's inputs are in flight while this row's transcendentals run.
+    const EpiClip<T> clip = epilogue_prepare_clip<T>(tile, lane, f.cols);
+
+    if (tile.kind == AT_EPI_PLAIN) {
+        T* ycol = f.Y + tile.out_col0 + 4 * lane;
+        for (int lr = 0; lr < nrows; lr += kPwRows) {
+            T a[kPwRows][4];
+            bool masked[kPwRows];
+#pragma unroll
+            for (int j = 0; j < kPwRows; ++j) {
+                masked[j] = false;
+                if (lr + j < nrows) {
+                    load4(xcol + static_cast<size_t>(r0 + lr + j) * f.ldx, a[j][0], a[j][1], a[j][2], a[j][3]);
+                    if (any_mask) masked[j] = f.row_mask[r0 + lr + j] != 0;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kPwRows; ++j)
+                if (lr + j < nrows) {
+                    if (tile.flags_any != 0) clip_mask_n<T, 4, true>(a[j], 0, f.cols, &clip, masked[j]);
+                    store4(ycol + static_cast<size_t>(r0 + lr + j) * f.ldy, a[j][0], a[j][1], a[j][2], a[j][3]);
+                }
+        }
+        return;
+    }
+
+    const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
     T n0, n1, n2, n3;
     bool nmask = false;
-    load4(xcol + static_cast<size_t>(r0 + warp) * f.ldx, n0, n1, n2, n3);
-    if (any_mask) nmask = f.row_mask[r0 + warp] != 0;
-    for (int lr = warp; lr < nrows; lr += kWarps) {
+    load4(xcol + static_cast<size_t>(r0) * f.ldx, n0, n1, n2, n3);
+    if (any_mask) nmask = f.row_mask[r0] != 0;
+#pragma unroll 1
+    for (int lr = 0; lr < nrows; ++lr) {
         const long long row = r0 + lr;
         const T a0 = n0, a1 = n1, a2 = n2, a3 = n3;
         const bool masked = nmask;
-        if (lr + kWarps < nrows) {
-            load4(xcol + static_cast<size_t>(row + kWarps) * f.ldx, n0, n1, n2, n3);
-            if (any_mask) nmask = f.row_mask[row + kWarps] != 0;
+        if (lr + 1 < nrows) {
+            load4(xcol + static_cast<size_t>(row + 1) * f.ldx, n0, n1, n2, n3);
+            if (any_mask) nmask = f.row_mask[row + 1] != 0;
         }
-        epilogue_store<T>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy);
+        epilogue_store<T, true>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
     }
 }
 
@@ -994,10 +1031,11 @@ static int launch_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void
     f.ldx = static_cast<size_t>(ldx);
     f.ldy = static_cast<size_t>(ldy);
     f.n_rows = n_rows;
-    f.rows_per_cta = 4 * kWarps;
+    f.rows_per_cta = 32;
+    f.n_tiles = epi->n_tiles;
     const int64_t gx = (n_rows + f.rows_per_cta - 1) / f.rows_per_cta;
     if (gx >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_pointwise: too many rows");
-    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(epi->n_tiles));
+    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((epi->n_tiles + kWarps - 1) / kWarps));
     pointwise_kernel<T><<<grid, kThreads, 0, st>>>(f);
     AT_LAUNCH_CHECK("pointwise_kernel");
     return AT_OK;
