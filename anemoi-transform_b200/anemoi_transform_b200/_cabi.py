@@ -21,6 +21,15 @@ AT_F32, AT_F64 = 0, 1
 AT_I32, AT_I64 = 0, 1
 
 EPI_PLAIN, EPI_UV2DDFF, EPI_DDFF2UV, EPI_QT2R, EPI_QT2QTR, EPI_RT2Q, EPI_RT2RTQ = range(7)
+EPI_AFFINE, EPI_AFFINE_INV, EPI_EXP, EPI_LOG, EPI_IMPUTE_NAN, EPI_COSSIN, EPI_ATAN2 = range(7, 14)
+EPI_RT2D, EPI_RT2RTD, EPI_DT2R, EPI_DT2DTR = range(14, 18)
+# outputs per 4 input columns of each kind
+EPI_OUT_PER_GROUP = {
+    EPI_PLAIN: 4, EPI_UV2DDFF: 4, EPI_DDFF2UV: 4, EPI_QT2R: 2, EPI_QT2QTR: 6, EPI_RT2Q: 2, EPI_RT2RTQ: 6,
+    EPI_AFFINE: 4, EPI_AFFINE_INV: 4, EPI_EXP: 4, EPI_LOG: 4, EPI_IMPUTE_NAN: 4, EPI_COSSIN: 8, EPI_ATAN2: 2,
+    EPI_RT2D: 2, EPI_RT2RTD: 6, EPI_DT2R: 2, EPI_DT2DTR: 6,
+}  # fmt: skip
+CMP_NOT_NAN = 6
 COL_CLIP_LO, COL_CLIP_HI, COL_MASK = 1, 2, 4
 
 
@@ -37,7 +46,7 @@ class NativeCallError(RuntimeError):
 
 
 class EpiSegment(Structure):
-    _fields_ = [("kind", c_int32), ("in_col", c_int32), ("n_in", c_int32), ("out_col", c_int32)]
+    _fields_ = [("kind", c_int32), ("in_col", c_int32), ("n_in", c_int32), ("out_col", c_int32), ("pa", c_double), ("pb", c_double)]
 
 
 class EpiCol(Structure):
@@ -64,6 +73,8 @@ PROTOTYPES = {
     "at_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "at_gather_cols": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "at_compare_mask": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p]),
+    "at_sum_cols": (c_int, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "at_range_flags": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_int, c_double, c_double, c_void_p, c_void_p]),
     "at_pipeline_create": (c_int, [c_void_p, c_int32, POINTER(c_void_p)]),
     "at_pipeline_destroy": (c_int, [c_void_p]),
     "at_pipeline_regrid": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64]),

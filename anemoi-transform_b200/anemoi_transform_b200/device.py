@@ -155,11 +155,12 @@ class CsrMatrix:
 class Epilogue:
     """A fused pointwise program (segments + per-output-column parameters)."""
 
-    def __init__(self, segments: Iterable[tuple[int, int, int, int]], cols: Iterable[tuple[float, float, float, int]]):
+    def __init__(self, segments: Iterable[tuple], cols: Iterable[tuple[float, float, float, int]]):
+        """segments: (kind, in_col, n_in, out_col[, pa, pb]); cols: (lo, hi, pressure, flags) per output column."""
         require_cuda()
-        segs = list(segments)
+        segs = [tuple(s) + (0.0, 0.0)[len(s) - 4 :] for s in segments]
         cols = list(cols)
-        seg_arr = (EpiSegment * len(segs))(*[EpiSegment(*map(int, s)) for s in segs])
+        seg_arr = (EpiSegment * len(segs))(*[EpiSegment(int(s[0]), int(s[1]), int(s[2]), int(s[3]), float(s[4]), float(s[5])) for s in segs])
         col_arr = (EpiCol * len(cols))(*[EpiCol(float(lo), float(hi), float(p), int(fl), 0) for lo, hi, p, fl in cols])
         h = c_void_p()
         call("at_epilogue_create", seg_arr, len(segs), col_arr, len(cols), byref(h))
@@ -323,6 +324,28 @@ def gather_cols(X, cols: Sequence[int], out=None):
     index = torch.tensor(list(cols), dtype=torch.int32, device=X.device)
     call("at_gather_cols", _ptr(index), n_out, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), X.element_size(), stream_ptr())
     return out
+
+
+def sum_cols(X, cols: Sequence[int], n_groups: int, n_terms: int, out=None):
+    """out[:, g] = X[:, cols[g*n_terms]] + X[:, cols[g*n_terms+1]] + … (sequential, X's dtype)."""
+    torch = _torch()
+    if len(cols) != n_groups * n_terms or any(c < 0 or c >= X.shape[1] for c in cols):
+        raise IndexError("sum_cols: bad column list")
+    if out is None:
+        out = torch.zeros((X.shape[0], round_up(n_groups, 4)), dtype=X.dtype, device=X.device)
+    index = torch.tensor(list(cols), dtype=torch.int32, device=X.device)
+    code = AT_F32 if X.dtype == torch.float32 else AT_F64
+    call("at_sum_cols", _ptr(index), n_groups, n_terms, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, stream_ptr())
+    return out
+
+
+def range_flags(X, first_col: int, n_cols: int, lo: float, hi: float) -> list[int]:
+    """Per column: bit 0 any value < lo, bit 1 any value > hi, bit 2 any NaN."""
+    torch = _torch()
+    flags = torch.zeros((max(n_cols, 1),), dtype=torch.int32, device=X.device)
+    code = AT_F32 if X.dtype == torch.float32 else AT_F64
+    call("at_range_flags", _ptr(X), X.stride(0), X.shape[0], int(first_col), int(n_cols), code, float(lo), float(hi), _ptr(flags), stream_ptr())
+    return [int(v) for v in flags[:n_cols].cpu().tolist()]
 
 
 def compare_mask(values, op: int, threshold: float):

@@ -18,8 +18,16 @@ filter_registry = Registry(__name__, entry_point_group="anemoi.transform.filters
 # importing the modules runs their registration decorators
 from .fields import apply_mask as _apply_mask  # noqa: E402,F401
 from .fields import clipper as _clipper  # noqa: E402,F401
+from .fields import cos_sin_from_rad as _cos_sin_from_rad  # noqa: E402,F401
+from .fields import cos_sin_mean_wave_direction as _cos_sin_mwd  # noqa: E402,F401
+from .fields import dewpoint as _dewpoint  # noqa: E402,F401
+from .fields import impute_nans as _impute_nans_fields  # noqa: E402,F401
+from .fields import lnsp_to_sp as _lnsp_to_sp  # noqa: E402,F401
 from .fields import q_to_r as _q_to_r  # noqa: E402,F401
 from .fields import regrid as _regrid  # noqa: E402,F401
+from .fields import remove_nans as _remove_nans_fields  # noqa: E402,F401
+from .fields import rescale as _rescale  # noqa: E402,F401
+from .fields import sum as _sum  # noqa: E402,F401
 from .fields import uv_to_ddff as _uv_to_ddff  # noqa: E402,F401
 
 
@@ -49,6 +57,8 @@ def create_filter(context: Any, config: Any):
 _merge_registries()
 
 from . import clip as _clip  # noqa: E402,F401
+from . import impute_nans as _impute_nans  # noqa: E402,F401
 from . import mask as _mask  # noqa: E402,F401
+from . import remove_nans as _remove_nans  # noqa: E402,F401
 
 __all__ = ["filter_registry", "create_filter", "create_filter_by_name"]

@@ -6,6 +6,8 @@
 //   regrid.py:380  `data[..., self.nearest_grid_points]`  (ScipyKDTreeNearestNeighbours)
 //   regrid.py:420  `data[..., self.mask]`                  (MaskedRegrid)
 //   apply_mask.py:160-163  `OPERATORS[op](mask_values, threshold)` / `mask_values == mask_value`
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace at {
@@ -92,9 +94,48 @@ __global__ void compare_mask_kernel(const T* __restrict__ values, size_t stride,
         case 2: m = v > thr; break;
         case 3: m = v >= thr; break;
         case 4: m = v < thr; break;
-        default: m = v <= thr; break;
+        case 5: m = v <= thr; break;
+        default: m = v == v; break;  // 6: not NaN
     }
     mask[i] = m ? 1 : 0;
+}
+
+// Y[r, g] = sum over the group's columns in order, starting from the first term (numpy's
+// `s = c0; s += c1; ...`, sum.py:109-115).  One warp per row, lanes over groups.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    sum_cols_kernel(const int* __restrict__ cols, int n_groups, int n_terms, const T* __restrict__ X, size_t ldx,
+                    T* __restrict__ Y, size_t ldy, long long n_rows) {
+    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const T* xr = X + static_cast<size_t>(row) * ldx;
+    T* yr = Y + static_cast<size_t>(row) * ldy;
+    for (int g = threadIdx.x & 31; g < n_groups; g += 32) {
+        T s = __ldg(xr + __ldg(cols + g * n_terms));
+        for (int k = 1; k < n_terms; ++k) s = s + __ldg(xr + __ldg(cols + g * n_terms + k));
+        yr[g] = s;
+    }
+}
+
+// flags[j] |= 1 (any < lo) | 2 (any > hi) | 4 (any NaN) over the rows of column first_col + j.
+// One warp per row chunk; lanes over columns; a warp ORs its findings once at the end.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    range_flags_kernel(const T* __restrict__ X, size_t ldx, long long n_rows, int first_col, int n_cols, T lo, T hi,
+                       unsigned* __restrict__ flags) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    const long long n_warps = static_cast<long long>(gridDim.x) * 8;
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const int c = c0 + lane;
+        unsigned f = 0;
+        if (c < n_cols)
+            for (long long r = warp; r < n_rows; r += n_warps) {
+                const T v = __ldg(X + static_cast<size_t>(r) * ldx + first_col + c);
+                f |= (v < lo ? 1u : 0u) | (v > hi ? 2u : 0u) | (v != v ? 4u : 0u);
+            }
+        if (f != 0) atomicOr(flags + c, f);
+    }
 }
 
 template <typename T>
@@ -186,7 +227,7 @@ extern "C" int at_compare_mask(const void* values, int dtype, int64_t stride, in
                                double threshold, uint8_t* mask, void* stream) {
     AT_REQUIRE(values != nullptr && mask != nullptr, "at_compare_mask: null argument");
     AT_REQUIRE(dtype == AT_F32 || dtype == AT_F64, "at_compare_mask: bad dtype code");
-    AT_REQUIRE(op >= 0 && op <= 5, "at_compare_mask: unknown operator %d", op);
+    AT_REQUIRE(op >= 0 && op <= 6, "at_compare_mask: unknown operator %d", op);
     AT_REQUIRE(n >= 0 && stride >= 1, "at_compare_mask: bad shape");
     if (n == 0) return AT_OK;
     const int64_t blocks = (n + 255) / 256;
@@ -199,5 +240,44 @@ extern "C" int at_compare_mask(const void* values, int dtype, int64_t stride, in
         compare_mask_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
             static_cast<const double*>(values), static_cast<size_t>(stride), n, op, threshold, mask);
     AT_LAUNCH_CHECK("compare_mask_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_sum_cols(const int32_t* cols, int32_t n_groups, int32_t n_terms, int64_t n_rows, const void* X,
+                           int64_t ldx, void* Y, int64_t ldy, int dtype, void* stream) {
+    AT_REQUIRE(cols != nullptr && X != nullptr && Y != nullptr, "at_sum_cols: null argument");
+    AT_REQUIRE(dtype == AT_F32 || dtype == AT_F64, "at_sum_cols: bad dtype code");
+    AT_REQUIRE(n_groups >= 0 && n_terms >= 1 && n_rows >= 0 && ldy >= n_groups, "at_sum_cols: bad shape");
+    if (n_groups == 0 || n_rows == 0) return AT_OK;
+    const int64_t blocks = (n_rows + 7) / 8;
+    AT_REQUIRE(blocks < (1ll << 31), "at_sum_cols: too many rows");
+    if (dtype == AT_F32)
+        sum_cols_kernel<float><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            cols, n_groups, n_terms, static_cast<const float*>(X), static_cast<size_t>(ldx), static_cast<float*>(Y),
+            static_cast<size_t>(ldy), n_rows);
+    else
+        sum_cols_kernel<double><<<static_cast<unsigned>(blocks), 256, 0, as_stream(stream)>>>(
+            cols, n_groups, n_terms, static_cast<const double*>(X), static_cast<size_t>(ldx), static_cast<double*>(Y),
+            static_cast<size_t>(ldy), n_rows);
+    AT_LAUNCH_CHECK("sum_cols_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_range_flags(const void* X, int64_t ldx, int64_t n_rows, int32_t first_col, int32_t n_cols, int dtype,
+                              double lo, double hi, uint32_t* flags, void* stream) {
+    AT_REQUIRE(X != nullptr && flags != nullptr, "at_range_flags: null argument");
+    AT_REQUIRE(dtype == AT_F32 || dtype == AT_F64, "at_range_flags: bad dtype code");
+    AT_REQUIRE(n_rows >= 0 && first_col >= 0 && n_cols >= 0 && ldx >= first_col + n_cols, "at_range_flags: bad shape");
+    if (n_rows == 0 || n_cols == 0) return AT_OK;
+    const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n_rows + 7) / 8, 8 * sm_count()));
+    if (dtype == AT_F32)
+        // numpy compares a float32 array with a Python scalar in float32 (NEP 50)
+        range_flags_kernel<float><<<blocks, 256, 0, as_stream(stream)>>>(
+            static_cast<const float*>(X), static_cast<size_t>(ldx), n_rows, first_col, n_cols, static_cast<float>(lo),
+            static_cast<float>(hi), flags);
+    else
+        range_flags_kernel<double><<<blocks, 256, 0, as_stream(stream)>>>(
+            static_cast<const double*>(X), static_cast<size_t>(ldx), n_rows, first_col, n_cols, lo, hi, flags);
+    AT_LAUNCH_CHECK("range_flags_kernel");
     return AT_OK;
 }

@@ -890,14 +890,19 @@ extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_se
     int n_in_cols = 0;
     for (int s = 0; s < n_segments; ++s) {
         const at_epi_segment_t& g = segments[s];
-        AT_REQUIRE(g.kind >= AT_EPI_PLAIN && g.kind <= AT_EPI_RT2RTQ,
+        AT_REQUIRE(g.kind >= AT_EPI_PLAIN && g.kind < AT_EPI_KIND_COUNT,
                    "at_epilogue_create: segment %d has unknown kind %d", s, g.kind);
         AT_REQUIRE(g.in_col >= 0 && g.in_col % 4 == 0 && g.n_in > 0 && g.n_in % 4 == 0,
                    "at_epilogue_create: segment %d: in_col and n_in must be multiples of 4", s);
-        int out_per_vec = 4;
-        if (g.kind == AT_EPI_QT2R || g.kind == AT_EPI_RT2Q) out_per_vec = 2;
-        if (g.kind == AT_EPI_QT2QTR || g.kind == AT_EPI_RT2RTQ) out_per_vec = 6;
-        const int align = g.kind == AT_EPI_PLAIN || g.kind == AT_EPI_UV2DDFF || g.kind == AT_EPI_DDFF2UV ? 4 : 2;
+        AT_REQUIRE(g.kind != AT_EPI_AFFINE_INV || g.pa != 0.0, "at_epilogue_create: segment %d: zero scale", s);
+        int out_per_vec = 4;  // outputs per 4 input columns
+        switch (g.kind) {
+            case AT_EPI_QT2R: case AT_EPI_RT2Q: case AT_EPI_ATAN2: case AT_EPI_RT2D: case AT_EPI_DT2R: out_per_vec = 2; break;
+            case AT_EPI_QT2QTR: case AT_EPI_RT2RTQ: case AT_EPI_RT2RTD: case AT_EPI_DT2DTR: out_per_vec = 6; break;
+            case AT_EPI_COSSIN: out_per_vec = 8; break;
+            default: break;
+        }
+        const int align = out_per_vec == 2 || out_per_vec == 6 ? 2 : 4;
         AT_REQUIRE(g.out_col >= 0 && g.out_col % align == 0,
                    "at_epilogue_create: segment %d: out_col must be a multiple of %d", s, align);
         const int n_vec = g.n_in / 4;
@@ -910,6 +915,9 @@ extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_se
             t.n_vec = std::min(kWarp, n_vec - v0);
             t.out_col0 = g.out_col + v0 * out_per_vec;
             t.flags_any = 0;
+            t.reserved = 0;
+            t.pa = g.pa;
+            t.pb = g.pb;
             for (int c = t.out_col0; c < t.out_col0 + t.n_vec * out_per_vec; ++c)
                 t.flags_any |= static_cast<int32_t>(cols[c].flags & (AT_COL_CLIP_LO | AT_COL_CLIP_HI | AT_COL_MASK));
             tiles.push_back(t);

@@ -110,6 +110,21 @@ AT_API int at_spmm(const at_csr_t* csr,
  *   AT_EPI_QT2QTR    in (q, t)     -> out (q, t, r)       q_to_r.py:69-73, return_inputs="all"
  *   AT_EPI_RT2Q      in (r, t)     -> out (q)             q_to_r.py:75-81
  *   AT_EPI_RT2RTQ    in (r, t)     -> out (r, t, q)       q_to_r.py:75-81, return_inputs="all"
+ *   AT_EPI_AFFINE    in (x)        -> out (x*pa + pb)     rescale.py:25-26   (Rescale / Convert forward)
+ *   AT_EPI_AFFINE_INV in (x)       -> out ((x-pb)/pa)     rescale.py:28-29   (backward)
+ *   AT_EPI_EXP       in (x)        -> out (exp x)         lnsp_to_sp.py:47-49
+ *   AT_EPI_LOG       in (x)        -> out (log x)         lnsp_to_sp.py:65-67
+ *   AT_EPI_IMPUTE_NAN in (x)       -> out (isnan x ? pa : x)  impute_nans.py:52-54
+ *   AT_EPI_COSSIN    in (x)        -> out (cos(x*pa), sin(x*pa))   cos_sin_from_rad.py:78-79 (pa = 1),
+ *                                                          cos_sin_mean_wave_direction.py:71-74 (pa = deg2rad(1))
+ *   AT_EPI_ATAN2     in (c, s)     -> out (atan2(s, c)*pa), wrapped into [0, 360) when pb != 0
+ *                                                          cos_sin_from_rad.py:100, cos_sin_mean_wave_direction.py:96-98
+ *   AT_EPI_RT2D      in (r, t)     -> out (td)            dewpoint.py:62-67 (r == 0 -> 1e-4 first)
+ *   AT_EPI_RT2RTD    in (r, t)     -> out (r, t, td)      dewpoint.py, return_inputs="all"
+ *   AT_EPI_DT2R      in (td, t)    -> out (r)             dewpoint.py:69-74
+ *   AT_EPI_DT2DTR    in (td, t)    -> out (td, t, r)      dewpoint.py, return_inputs="all"
+ * pa / pb are per-segment constants (a filter instance applies one scale / offset / value to
+ * every field it selects); on the float32 path they are rounded to float32 (NEP 50).
  *
  * After the kind's conversion every OUTPUT column c applies, in this order,
  *   clip:  np.clip(x, lo, hi) with NaN passing through     clipper.py:67-70
@@ -123,6 +138,18 @@ AT_API int at_spmm(const at_csr_t* csr,
 #define AT_EPI_QT2QTR 4
 #define AT_EPI_RT2Q 5
 #define AT_EPI_RT2RTQ 6
+#define AT_EPI_AFFINE 7
+#define AT_EPI_AFFINE_INV 8
+#define AT_EPI_EXP 9
+#define AT_EPI_LOG 10
+#define AT_EPI_IMPUTE_NAN 11
+#define AT_EPI_COSSIN 12
+#define AT_EPI_ATAN2 13
+#define AT_EPI_RT2D 14
+#define AT_EPI_RT2RTD 15
+#define AT_EPI_DT2R 16
+#define AT_EPI_DT2DTR 17
+#define AT_EPI_KIND_COUNT 18
 
 #define AT_COL_CLIP_LO 1u /* lo is set  */
 #define AT_COL_CLIP_HI 2u /* hi is set  */
@@ -132,7 +159,8 @@ typedef struct {
     int32_t kind;    /* AT_EPI_*                                                        */
     int32_t in_col;  /* first input column; multiple of 4                               */
     int32_t n_in;    /* input columns in the segment (even for pair kinds)              */
-    int32_t out_col; /* first output column; multiple of 2 (of 4 for PLAIN)             */
+    int32_t out_col; /* first output column; multiple of 2 (of 4 for 1:1 and 1:2 kinds) */
+    double pa, pb;   /* per-segment constants of the kind (see the table above)         */
 } at_epi_segment_t;
 
 typedef struct {
@@ -182,10 +210,21 @@ AT_API int at_gather_rows(const int64_t* idx, int64_t n_out, int64_t n_src,
 AT_API int at_gather_cols(const int32_t* cols, int32_t n_out, int64_t n_rows, const void* X, int64_t ldx,
                    void* Y, int64_t ldy, int elem_size, void* stream);
 /* mask[i] = OP(values[i], threshold) — MaskVariable._compute_mask apply_mask.py:160-163.
- * op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=.  values: device f32 / f64 (dtype) with element
+ * op: 0 ==, 1 !=, 2 >, 3 >=, 4 <, 5 <=, 6 "is not NaN" (threshold unused; `~np.isnan(data)`,
+ * remove_nans.py:103).  values: device f32 / f64 (dtype) with element
  * stride `stride`; a float32 array is compared in float32, as numpy does (NEP 50). */
 AT_API int at_compare_mask(const void* values, int dtype, int64_t stride, int64_t n, int op,
                     double threshold, uint8_t* mask, void* stream);
+/* Y[r, g] = ((X[r, cols[g*n_terms]] + X[r, cols[g*n_terms+1]]) + ...) for g < n_groups: the
+ * `sum` filter's `s += c` over its params in field order (sum.py:109-115), one output column
+ * per group.  cols: device int32[n_groups * n_terms].  dtype AT_F32 | AT_F64. */
+AT_API int at_sum_cols(const int32_t* cols, int32_t n_groups, int32_t n_terms, int64_t n_rows,
+                const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype, void* stream);
+/* flags[j] |= 1 if any X[r, first_col + j] < lo, 2 if any > hi, 4 if any is NaN, for
+ * j < n_cols: the range validation of cos_sin_from_rad.py:74-77 without a host round trip.
+ * flags: device uint32[n_cols], zeroed by the caller. */
+AT_API int at_range_flags(const void* X, int64_t ldx, int64_t n_rows, int32_t first_col, int32_t n_cols,
+                   int dtype, double lo, double hi, uint32_t* flags, void* stream);
 
 /* ------------------------------------------------ end-to-end host pipeline ----------- */
 /*

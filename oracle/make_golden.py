@@ -6,6 +6,10 @@ TEST INFRASTRUCTURE, build container only.  Run:   python oracle/make_golden.py
 What is pinned by these files
     spatial_*.npz    reference spatial.py on live scipy cKDTree (real arithmetic of the path)
     regrid_*.npz     reference RegridFilter (MIRMatrix / nearest / mask) on live scipy.sparse
+    filters_more.npz reference Rescale / LnspToSp / ImputeNaNs / RemoveNaNs / CosSinFromRad /
+                     CosSinWaveDirection / DewPoint / Sum, same caveat for the
+                     dewpoint VALUES (earthkit-meteo → oracle/pointwise.py, pinned by the
+                     reference's test_dewpoint.py:23-27)
     filters.npz      reference WindComponents / HumidityConversion / Clipper / MaskVariable:
                      grouping, output ordering, metadata and dtypes are the reference's; the
                      wind / humidity VALUES come from oracle/pointwise.py through the
@@ -179,6 +183,90 @@ def filter_cases(mods, syn, ekd):
     print("filters.npz:", {k: v.shape for k, v in out.items()})
 
 
+def more_filter_cases(mods, syn, ekd):
+    """SURVEY §8(f) rank 1 — rescale, lnsp_to_sp, impute_nans, remove_nans, cos_sin_*, dewpoint,
+    sum — run through the reference's own classes (values of the dewpoint pair come from
+    oracle/pointwise.py via the earthkit.meteo stub; pinned by test_dewpoint.py:23-27)."""
+    rng = np.random.default_rng(23)
+    lat = np.linspace(50, -50, 21)
+    lon = np.linspace(0, 340, 18)
+    n = lat.size * lon.size
+    LAT, LON = (a.reshape(-1) for a in np.meshgrid(lat, lon, indexing="ij"))
+
+    def fl(specs):
+        # fresh arrays per call: the reference's DewPoint writes 1e-4 into the r == 0 points of the
+        # array it is handed (dewpoint.py:63-64), which must not leak into the next case
+        return _fieldlist(ekd, [(p, lev, v.copy()) for p, lev, v in specs], LAT, LON)
+
+    out, order = {}, {}
+
+    def record(name, result):
+        order[name] = [[f.metadata("param"), None if f.metadata("levelist") is None else int(f.metadata("levelist")), str(f.to_numpy().dtype)] for f in result]
+        out[name] = np.stack([f.to_numpy(flatten=True).astype(np.float64) for f in result])
+
+    def nanspots(a, k):
+        a = a.copy()
+        a[rng.choice(a.size, k, replace=False)] = np.nan
+        return a
+
+    t = {lev: rng.normal(270, 20, n).astype(np.float32) for lev in (500, 850)}
+    r = {lev: rng.uniform(0, 110, n).astype(np.float32) for lev in (500, 850)}
+    r[850][:3] = [0.0, 100.0, np.nan]
+    t[850][:6] = [280.0, 280.0, 280.0, np.nan, 273.16, 32.19]
+    lnsp = rng.normal(11.5, 0.1, n).astype(np.float32)
+    lnsp[:4] = [np.nan, np.inf, -np.inf, 0.0]
+    mwd = rng.uniform(0, 360, n).astype(np.float32)
+    mwd[:5] = [0.0, 360.0, 180.0, 90.0, np.nan]
+    rad = rng.uniform(-np.pi, np.pi, n).astype(np.float32)
+    rad[:4] = [0.0, np.float32(np.pi), -np.float32(np.pi), np.nan]
+    sst = nanspots(rng.normal(290, 5, n).astype(np.float32), 40)
+    lsp, cp, sf = (np.abs(rng.normal(0, 1e-3, n)).astype(np.float32) for _ in range(3))
+    cp = nanspots(cp, 3)
+    mixed = [("t", 850, t[850]), ("r", 850, r[850]), ("lnsp", 1, lnsp), ("mwd", 0, mwd), ("rad", 0, rad), ("sst", 0, sst), ("r", 500, r[500]),
+             ("lsp", 0, lsp), ("t", 500, t[500]), ("cp", 0, cp), ("sf", 0, sf)]  # fmt: skip
+    out["in_values"] = np.stack([m[2] for m in mixed])
+    order["in"] = [[m[0], m[1]] for m in mixed]
+    out["lat"], out["lon"] = LAT, LON
+
+    rs = mods["rescale"].Rescale(param="t", scale=1.8, offset=-459.67)
+    fwd = rs.forward(fl(mixed))
+    record("rescale_fwd", fwd)
+    record("rescale_bwd", rs.backward(fwd))
+    ls = mods["lnsp_to_sp"].LnspToSp()
+    sp = ls.forward(fl(mixed))
+    record("lnsp_to_sp", sp)
+    record("sp_to_lnsp", ls.backward(sp))
+    record("impute_sst", mods["impute_nans"].ImputeNaNs(param=["sst", "cp"], value=-1.5).forward(fl(mixed)))
+    cs = mods["cos_sin_from_rad"].CosSinFromRad(param="rad")
+    c = cs.forward(fl(mixed))
+    record("cos_sin_from_rad", c)
+    record("rad_from_cos_sin", cs.backward(c))
+    cw = mods["cos_sin_mean_wave_direction"].CosSinWaveDirection()
+    c = cw.forward(fl(mixed))
+    record("cos_sin_mwd", c)
+    record("mwd_from_cos_sin", cw.backward(c))
+    dp = mods["dewpoint"].DewPoint()
+    d = dp.forward(fl(mixed))
+    record("r_to_d_all", d)
+    record("r_to_d_none", mods["dewpoint"].DewPoint(return_inputs="none").forward(fl(mixed)))
+    only_dt = [f for f in d if f.metadata("param") in ("d", "t")]
+    record("d_to_r_all", dp.backward(ekd.SimpleFieldList(only_dt)))
+    record("sum_tp", mods["sum"].Sum(params=["lsp", "cp", "sf"], output="tp").forward(fl(mixed)))
+    rn = mods["remove_nans"].RemoveNaNs(param="sst")
+    res = rn.forward(fl(mixed))
+    record("remove_nans_sst", res)
+    out["remove_nans_lat"], out["remove_nans_lon"] = res[0].grid_points()
+    # float64 fields keep float64
+    mixed64 = [(p, lev, val.astype(np.float64)) for p, lev, val in mixed]
+    record("rescale_fwd_f64", rs.forward(fl(mixed64)))
+    record("cos_sin_mwd_f64", cw.forward(fl(mixed64)))
+    record("mwd_from_cos_sin_f64", cw.backward(cw.forward(fl(mixed64))))
+    record("r_to_d_all_f64", dp.forward(fl(mixed64)))
+    record("sum_tp_f64", mods["sum"].Sum(params=["lsp", "cp", "sf"], output="tp").forward(fl(mixed64)))
+    np.savez_compressed(GOLDEN / "filters_more.npz", order=json.dumps(order), **out)
+    print("filters_more.npz:", {k: v.shape for k, v in out.items()})
+
+
 def main():
     import tempfile
 
@@ -192,6 +280,7 @@ def main():
     with tempfile.TemporaryDirectory() as tmp:
         regrid_cases(mods, syn, ekd, Path(tmp))
     filter_cases(mods, syn, ekd)
+    more_filter_cases(mods, syn, ekd)
 
 
 if __name__ == "__main__":

@@ -118,6 +118,31 @@ def specific_humidity_from_relative_humidity(t, r, p):
         return specific_humidity_from_vapour_pressure(e, p)
 
 
+def saturation_vapour_pressure_water(t):
+    """Water-phase Tetens formula (earthkit.meteo.thermo.array.saturation_vapour_pressure(t, phase="water"))."""
+    return _es_water(np.asarray(t))
+
+
+def temperature_from_saturation_vapour_pressure(es):
+    """Inverse of the water-phase formula (earthkit.meteo.thermo.array)."""
+    v = np.log(es / 611.21)
+    return (v * 32.19 - 17.502 * T0) / (v - 17.502)
+
+
+def dewpoint_from_relative_humidity(t, r):
+    """earthkit.meteo.thermo.dewpoint_from_relative_humidity, called at dewpoint.py:65.
+    PINNED by tests/field_filters/test_dewpoint.py:23-27 (tests/test_oracle_pointwise.py)."""
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        es = saturation_vapour_pressure_water(t) * r / 100.0
+        return temperature_from_saturation_vapour_pressure(es)
+
+
+def relative_humidity_from_dewpoint(t, td):
+    """earthkit.meteo.thermo.relative_humidity_from_dewpoint, called at dewpoint.py:73."""
+    with np.errstate(over="ignore", invalid="ignore", divide="ignore"):
+        return 100.0 * saturation_vapour_pressure_water(td) / saturation_vapour_pressure_water(t)
+
+
 def clip(data, minimum, maximum):
     """clipper.py:69."""
     return np.clip(data, minimum, maximum)

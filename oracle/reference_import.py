@@ -25,6 +25,15 @@ HOT_PATH_MODULES = (
     "anemoi.transform.filters.fields.q_to_r",
     "anemoi.transform.filters.fields.clipper",
     "anemoi.transform.filters.fields.apply_mask",
+    # the remaining pointwise field filters
+    "anemoi.transform.filters.fields.rescale",
+    "anemoi.transform.filters.fields.lnsp_to_sp",
+    "anemoi.transform.filters.fields.impute_nans",
+    "anemoi.transform.filters.fields.remove_nans",
+    "anemoi.transform.filters.fields.cos_sin_from_rad",
+    "anemoi.transform.filters.fields.cos_sin_mean_wave_direction",
+    "anemoi.transform.filters.fields.dewpoint",
+    "anemoi.transform.filters.fields.sum",
 )
 
 

@@ -108,3 +108,10 @@ def assert_close_to_range(actual, expected, rel=1e-6, what="", circular=None):
         rng = circular
     worst = diff.max()
     assert worst <= rel * rng, f"{what}: max |diff| {worst:.3e} > {rel:g} x range {rng:.3e}"
+
+
+@pytest.fixture(scope="session")
+def golden_filters_more():
+    d = dict(np.load(GOLDEN / "filters_more.npz"))
+    d["order"] = json.loads(str(d["order"]))
+    return d

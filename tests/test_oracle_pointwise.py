@@ -64,3 +64,62 @@ def test_filter_level_golden_is_the_oracle(golden_filters):
     r = pw.relative_humidity_from_specific_humidity(x[order[("t", 500)]], x[order[("q", 500)]], 50000.0)
     names = [tuple(o[:2]) for o in g["order"]["q_to_r_all"]]
     assert np.array_equal(g["q_to_r_all"][names.index(("r", 500))], r.astype(np.float64), equal_nan=True)
+
+
+# reference tests/field_filters/test_dewpoint.py:23-27
+R_DEW = [[78.13834333, 71.28598853], [99.17328572, 44.52144788], [56.49667261, 86.10495618]]
+T_DEW = [[298.42488098, 297.55574036], [278.68269348, 293.99324036], [300.61042786, 300.40144348]]
+D_DEW = [[294.34245300, 292.02214050], [278.56315613, 281.47135925], [291.19792175, 297.87370300]]
+
+
+def test_dewpoint_golden_vectors():
+    td = pw.dewpoint_from_relative_humidity(np.array(T_DEW), np.array(R_DEW))
+    assert np.allclose(td, D_DEW)
+    r = pw.relative_humidity_from_dewpoint(np.array(T_DEW), np.array(D_DEW))
+    assert np.allclose(r, R_DEW)
+    t32 = np.array(T_DEW, dtype=np.float32)
+    assert pw.dewpoint_from_relative_humidity(t32, np.array(R_DEW, dtype=np.float32)).dtype == np.float32
+
+
+def test_more_filters_golden_is_numpy_and_the_oracle(golden_filters_more):
+    """tests/golden/filters_more.npz (outputs of the reference's own filter classes) against
+    the plain numpy statements of reference rescale.py:25-29, lnsp_to_sp.py:48,66,
+    impute_nans.py:52-54, cos_sin_from_rad.py:78-79,100, cos_sin_mean_wave_direction.py:71-74,96-98,
+    sum.py:109-115, remove_nans.py:103-117, and the oracle's dewpoint formulas."""
+    g = golden_filters_more
+    x = {tuple(o): v.astype(np.float32) for o, v in zip(g["order"]["in"], g["in_values"])}
+
+    def got(name, param, lev):
+        names = [tuple(o[:2]) for o in g["order"][name]]
+        return g[name][names.index((param, lev))]
+
+    def same(a, b):
+        return np.array_equal(np.asarray(a, dtype=np.float64), b, equal_nan=True)
+
+    t = x[("t", 850)]
+    assert same(t * 1.8 + -459.67, got("rescale_fwd", "t", 850))
+    assert same(((t * 1.8 + -459.67) - -459.67) / 1.8, got("rescale_bwd", "t", 850))
+    with np.errstate(all="ignore"):
+        assert same(np.exp(x[("lnsp", 1)]), got("lnsp_to_sp", "sp", None))
+        assert same(np.log(np.exp(x[("lnsp", 1)])), got("sp_to_lnsp", "lnsp", None))
+    sst = x[("sst", 0)].copy()
+    sst[np.isnan(sst)] = -1.5
+    assert same(sst, got("impute_sst", "sst", 0))
+    rad, mwd = x[("rad", 0)], x[("mwd", 0)]
+    assert same(np.cos(rad), got("cos_sin_from_rad", "cos_rad", 0)) and same(np.sin(rad), got("cos_sin_from_rad", "sin_rad", 0))
+    assert same(np.arctan2(np.sin(rad), np.cos(rad)), got("rad_from_cos_sin", "rad", 0))
+    assert same(np.cos(np.deg2rad(mwd)), got("cos_sin_mwd", "cos_mwd", 0))
+    back = np.rad2deg(np.arctan2(np.sin(np.deg2rad(mwd)), np.cos(np.deg2rad(mwd))))
+    back = np.where(back >= 360, back - 360, back)
+    back = np.where(back < 0, back + 360, back)
+    assert same(back, got("mwd_from_cos_sin", "mwd", 0))
+    r = x[("r", 850)].copy()
+    r[r == 0] = 1.0e-4
+    assert same(pw.dewpoint_from_relative_humidity(t, r), got("r_to_d_all", "d", 850))
+    assert same(pw.relative_humidity_from_dewpoint(t, pw.dewpoint_from_relative_humidity(t, r)), got("d_to_r_all", "r", 850))
+    s = x[("lsp", 0)].copy()
+    s += x[("cp", 0)]
+    s += x[("sf", 0)]
+    assert same(s, got("sum_tp", "tp", 0))
+    keep = ~np.isnan(x[("sst", 0)])
+    assert same(x[("t", 500)][keep], got("remove_nans_sst", "t", 500)) and np.array_equal(g["remove_nans_lat"], g["lat"][keep])
