@@ -37,13 +37,16 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// One warp per output row and 16-byte chunk tile.
+// One warp per output row and 16-byte chunk tile.  blockIdx.x = row_block * tiles + tile: CTAs
+// that run together cover adjacent column tiles of the same rows, i.e. long contiguous spans
+// of each source row (DRAM page locality, as in spmm_f32_kernel's super-tiles).
 template <typename V>
 __global__ void __launch_bounds__(256)
     gather_rows_kernel(const long long* __restrict__ idx, long long n_out, long long n_src,
                        const V* __restrict__ X, size_t ldx, V* __restrict__ Y, size_t ldy,
-                       int n_vec, int* __restrict__ err_flag) {
-    const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+                       int n_vec, int tiles, int* __restrict__ err_flag) {
+    const long long row = static_cast<long long>(blockIdx.x / tiles) * 8 + (threadIdx.x >> 5);
+    const int tile = static_cast<int>(blockIdx.x % tiles);
     if (row >= n_out) return;
     const int lane = threadIdx.x & 31;
     const long long s = idx[row];
@@ -53,7 +56,7 @@ __global__ void __launch_bounds__(256)
     }
     const V* xr = X + static_cast<size_t>(s) * ldx;
     V* yr = Y + static_cast<size_t>(row) * ldy;
-    const int v0 = blockIdx.y * 128;
+    const int v0 = tile * 128;
     V tmp[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -154,13 +157,11 @@ static int launch_transpose(const void* src, int64_t rows, int64_t cols, int64_t
 template <typename V>
 static int launch_gather(const int64_t* idx, int64_t n_out, int64_t n_src, const void* X, int64_t ldx_v,
                          void* Y, int64_t ldy_v, int64_t n_vec, int32_t* err_flag, cudaStream_t st) {
-    const int64_t gx = (n_out + 7) / 8, gy = (n_vec + 127) / 128;
-    if (gx >= (1ll << 31) || gy > 65535) return set_error(AT_ERR_UNSUPPORTED, "at_gather_rows: too large");
-    dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
-    gather_rows_kernel<V><<<grid, 256, 0, st>>>(reinterpret_cast<const long long*>(idx), n_out, n_src,
-                                               static_cast<const V*>(X), static_cast<size_t>(ldx_v),
-                                               static_cast<V*>(Y), static_cast<size_t>(ldy_v),
-                                               static_cast<int>(n_vec), err_flag);
+    const int64_t tiles = (n_vec + 127) / 128, gx = (n_out + 7) / 8 * tiles;
+    if (gx >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_gather_rows: too large");
+    gather_rows_kernel<V><<<static_cast<unsigned>(gx), 256, 0, st>>>(
+        reinterpret_cast<const long long*>(idx), n_out, n_src, static_cast<const V*>(X), static_cast<size_t>(ldx_v),
+        static_cast<V*>(Y), static_cast<size_t>(ldy_v), static_cast<int>(n_vec), static_cast<int>(tiles), err_flag);
     AT_LAUNCH_CHECK("gather_rows_kernel");
     return AT_OK;
 }

@@ -251,66 +251,51 @@ struct FusedArgs {
     size_t ldy;  // in floats
 };
 
-template <int VPL, int UNNZ, bool FALLBACK>
-__global__ void __launch_bounds__(kThreads, VPL == 1 ? 4 : 2) spmm_fused_kernel(const FusedArgs f) {
+// One warp per target row, one entry of the tile table per CTA (32 lanes x 4 input columns,
+// CTA-uniform kind), 64 registers so 4 CTAs stay resident per SM.  Measured alternatives on
+// config 4 (fused uv_to_ddff / q_to_r / clip / mask, 4.2 ms): two table entries per CTA (epilogue
+// inlined twice, 116 registers, 2 CTAs / SM) 5.0 ms; two rows per warp step with one epilogue
+// copy (8 gathers in flight, spills at 64 registers) 5.9 ms, 4.3 ms at 80 registers / 3 CTAs.
+template <int UNNZ, bool FALLBACK, uint32_t FAM>
+__global__ void __launch_bounds__(kThreads, 4) spmm_fused_kernel(const FusedArgs f) {
     __shared__ __align__(16) int s_idx[kSegCap];
     __shared__ __align__(16) float s_w[kSegCap];
     __shared__ int s_ptr[kMaxRowsPerCta + 1];
     __shared__ __align__(8) uint64_t s_bar;
 
-    // Same grid order as spmm_f32_kernel; a CTA owns VPL consecutive entries of the tile table
-    // (each 32 lanes x 4 input columns, CTA-uniform kind), accumulated together so a lane has
-    // VPL x 4 gathers in flight per chunk.
+    // Same grid order as spmm_f32_kernel.
     const SpmmArgs& a = f.s;
-    const int group = blockIdx.y * a.super + static_cast<int>(blockIdx.x % a.super);
+    const int t_index = blockIdx.y * a.super + static_cast<int>(blockIdx.x % a.super);
     const int r0 = static_cast<int>(blockIdx.x / a.super) * a.rows_per_cta;
     const int nrows = min(a.rows_per_cta, a.n_rows - r0);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (group * VPL >= a.n_vec) return;  // n_vec = number of tile-table entries here
+    if (t_index >= a.n_vec) return;  // n_vec = number of tile-table entries here
 
-    EpiTile tile[VPL];
-    int vcol[VPL];
-    bool vok[VPL];
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        const int t = group * VPL + v;
-        tile[v] = f.tiles[min(t, a.n_vec - 1)];
-        vcol[v] = tile[v].in_vec0 + lane;
-        vok[v] = t < a.n_vec && lane < tile[v].n_vec;
-    }
+    const EpiTile tile = f.tiles[t_index];
+    int vcol[1] = {tile.in_vec0 + lane};
+    bool vok[1] = {lane < tile.n_vec};
 
     int seg_base;
     bool in_smem;
     stage_segment<UNNZ, UNNZ != 0, FALLBACK>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
 
-    EpiLane<float> lane_prm[VPL];
-    bool any_mask = false;
-#pragma unroll
-    for (int v = 0; v < VPL; ++v) {
-        lane_prm[v] = epilogue_prepare<float>(tile[v], lane, f.cols);
-        any_mask = any_mask || (tile[v].flags_any & AT_COL_MASK) != 0;
-    }
-    any_mask = any_mask && f.row_mask != nullptr;
+    const EpiLane<float> lane_prm = epilogue_prepare<float>(tile, lane, f.cols);
+    const bool any_mask = (tile.flags_any & AT_COL_MASK) != 0 && f.row_mask != nullptr;
 
     for (int lr = warp; lr < nrows; lr += kWarps) {
-        float4 acc[VPL];
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
         if constexpr (UNNZ > 0) {
-            accumulate_row<VPL, 4, true>(a, lr * UNNZ, (lr + 1) * UNNZ, s_idx, s_w, vcol, vok, acc);
+            accumulate_row<1, 4, true>(a, lr * UNNZ, (lr + 1) * UNNZ, s_idx, s_w, vcol, vok, acc);
         } else if (!FALLBACK || in_smem) {
-            accumulate_row<VPL, 4, true>(a, s_ptr[lr] - seg_base, s_ptr[lr + 1] - seg_base, s_idx,
-                                         s_w, vcol, vok, acc);
+            accumulate_row<1, 4, true>(a, s_ptr[lr] - seg_base, s_ptr[lr + 1] - seg_base, s_idx, s_w, vcol, vok, acc);
         } else {
-            accumulate_row<VPL, 4, false>(a, s_ptr[lr], s_ptr[lr + 1], s_idx, s_w, vcol, vok, acc);
+            accumulate_row<1, 4, false>(a, s_ptr[lr], s_ptr[lr + 1], s_idx, s_w, vcol, vok, acc);
         }
         const int row = r0 + lr;
         const bool masked = any_mask && f.row_mask[row] != 0;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v)
-            if (vok[v])
-                epilogue_store<float>(tile[v], lane, acc[v].x, acc[v].y, acc[v].z, acc[v].w, lane_prm[v], f.cols,
-                                      masked, f.Yf + static_cast<size_t>(row) * f.ldy);
+        if (vok[0])
+            epilogue_store<float, false, FAM>(tile, lane, acc[0].x, acc[0].y, acc[0].z, acc[0].w, lane_prm, f.cols, masked,
+                                              f.Yf + static_cast<size_t>(row) * f.ldy);
     }
 }
 
@@ -347,7 +332,7 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
 // row's load in flight behind it, 4 CTAs per SM.
 constexpr int kPwRows = 4;
 
-template <typename T>
+template <typename T, uint32_t FAM>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_kernel(const PointwiseArgs<T> f) {
     const long long r0 = static_cast<long long>(blockIdx.x) * f.rows_per_cta;
     const int nrows = static_cast<int>(min(static_cast<long long>(f.rows_per_cta), f.n_rows - r0));
@@ -397,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
             load4(xcol + static_cast<size_t>(row + 1) * f.ldx, n0, n1, n2, n3);
             if (any_mask) nmask = f.row_mask[row + 1] != 0;
         }
-        epilogue_store<T, true>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
+        epilogue_store<T, true, FAM>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
     }
 }
 
@@ -936,6 +921,7 @@ extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_se
         h64[static_cast<size_t>(c)] = {lo, hi, cols[c].pressure, cols[c].flags};
     }
     at_epilogue* e = new at_epilogue();
+    for (int sgm = 0; sgm < n_segments; ++sgm) e->kinds_mask |= kind_bit(segments[sgm].kind);
     e->n_tiles = static_cast<int32_t>(tiles.size());
     e->n_in_cols = n_in_cols;
     e->n_out_cols = n_out_cols;
@@ -997,30 +983,34 @@ extern "C" int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi, cons
     f.row_mask = row_mask;
     f.Yf = Y;
     f.ldy = static_cast<size_t>(ldy);
-    // One tile-table entry per CTA: at 64 registers 4 CTAs stay resident per SM.  Two entries per
-    // CTA (the epilogue inlined twice, 116 registers, 2 CTAs / SM) measured 5.0 ms against 4.2 ms
-    // on config 4.
-    constexpr int VPL = 1;
-    const int groups = (epi->n_tiles + VPL - 1) / VPL;
+    const int groups = epi->n_tiles;
     // widest super-tile whose live source rows stay in L2 (see at_spmm)
-    const int super_fit = static_cast<int>(64.0e6 / (2.0 * std::max(1.0, csr->live_cols) * 512.0 * VPL));
+    const int super_fit = static_cast<int>(64.0e6 / (2.0 * std::max(1.0, csr->live_cols) * 512.0));
     f.s.super = std::max(1, std::min({super_fit, groups, 63}));
     const int64_t row_blocks = (csr->n_rows + f.s.rows_per_cta - 1) / f.s.rows_per_cta;
     const int64_t gx64 = row_blocks * f.s.super, gy64 = (groups + f.s.super - 1) / f.s.super;
     if (gy64 > 65535 || gx64 >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_spmm_fused: grid too large");
     dim3 grid(static_cast<unsigned>(gx64), static_cast<unsigned>(gy64));
-#define AT_FUSED_LAUNCH(V)                                                                        \
-    do {                                                                                          \
-        if (csr->uniform_nnz == 4)                                                                \
-            spmm_fused_kernel<V, 4, false><<<grid, kThreads, 0, as_stream(stream)>>>(f);          \
-        else if (csr->uniform_nnz == 12)                                                          \
-            spmm_fused_kernel<V, 12, false><<<grid, kThreads, 0, as_stream(stream)>>>(f);         \
-        else if (csr->max_seg64 <= kSegCap)                                                       \
-            spmm_fused_kernel<V, 0, false><<<grid, kThreads, 0, as_stream(stream)>>>(f);          \
-        else                                                                                      \
-            spmm_fused_kernel<V, 0, true><<<grid, kThreads, 0, as_stream(stream)>>>(f);           \
+#define AT_FUSED_LAUNCH(FAM)                                                                       \
+    do {                                                                                           \
+        if (csr->uniform_nnz == 4)                                                                 \
+            spmm_fused_kernel<4, false, FAM><<<grid, kThreads, 0, as_stream(stream)>>>(f);    \
+        else if (csr->uniform_nnz == 12)                                                           \
+            spmm_fused_kernel<12, false, FAM><<<grid, kThreads, 0, as_stream(stream)>>>(f);   \
+        else if (csr->max_seg64 <= kSegCap)                                                        \
+            spmm_fused_kernel<0, false, FAM><<<grid, kThreads, 0, as_stream(stream)>>>(f);    \
+        else                                                                                       \
+            spmm_fused_kernel<0, true, FAM><<<grid, kThreads, 0, as_stream(stream)>>>(f);     \
     } while (0)
-    AT_FUSED_LAUNCH(VPL);
+    // the smallest kind family that holds the program (epilogue.cuh)
+    if ((epi->kinds_mask & ~FAM_BASIC) == 0)
+        AT_FUSED_LAUNCH(FAM_BASIC);
+    else if ((epi->kinds_mask & ~FAM_UNARY) == 0)
+        AT_FUSED_LAUNCH(FAM_UNARY);
+    else if ((epi->kinds_mask & ~FAM_TRIG) == 0)
+        AT_FUSED_LAUNCH(FAM_TRIG);
+    else
+        AT_FUSED_LAUNCH(FAM_ALL);
 #undef AT_FUSED_LAUNCH
     AT_LAUNCH_CHECK("spmm_fused_kernel");
     return AT_OK;
@@ -1044,7 +1034,14 @@ static int launch_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void
     const int64_t gx = (n_rows + f.rows_per_cta - 1) / f.rows_per_cta;
     if (gx >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_pointwise: too many rows");
     dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((epi->n_tiles + kWarps - 1) / kWarps));
-    pointwise_kernel<T><<<grid, kThreads, 0, st>>>(f);
+    if ((epi->kinds_mask & ~FAM_BASIC) == 0)
+        pointwise_kernel<T, FAM_BASIC><<<grid, kThreads, 0, st>>>(f);
+    else if ((epi->kinds_mask & ~FAM_UNARY) == 0)
+        pointwise_kernel<T, FAM_UNARY><<<grid, kThreads, 0, st>>>(f);
+    else if ((epi->kinds_mask & ~FAM_TRIG) == 0)
+        pointwise_kernel<T, FAM_TRIG><<<grid, kThreads, 0, st>>>(f);
+    else
+        pointwise_kernel<T, FAM_ALL><<<grid, kThreads, 0, st>>>(f);
     AT_LAUNCH_CHECK("pointwise_kernel");
     return AT_OK;
 }
