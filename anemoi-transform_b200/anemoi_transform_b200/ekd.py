@@ -89,6 +89,17 @@ class Metadata:
         return Metadata(d, self.geography, self._mars)
 
 
+class _ForeignMetadata(Metadata):
+    """Adapter around a dict-like metadata object that implements `as_namespace` itself."""
+
+    def __init__(self, inner: Any):
+        super().__init__({k: inner[k] for k in inner.keys()}, getattr(inner, "geography", None), False)
+        self._inner = inner
+
+    def as_namespace(self, namespace: str | None = None) -> dict[str, Any]:
+        return dict(self._inner.as_namespace(namespace))
+
+
 class Field:
     """Base class of fields (earthkit.data.Field)."""
 
@@ -100,6 +111,10 @@ class ArrayField(Field):
         self._array = np.asarray(array)
         if isinstance(metadata, Metadata):
             self._metadata = metadata
+        elif hasattr(metadata, "as_namespace"):
+            # a dict-like metadata object that brings its own namespaces (earthkit's RawMetadata /
+            # UserMetadata subclasses): keep its as_namespace
+            self._metadata = _ForeignMetadata(metadata)
         else:
             geography = None
             if latitudes is not None and longitudes is not None:

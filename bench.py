@@ -432,7 +432,17 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def reserve_stdout():
+    """Keep the process's real stdout for the one JSON line: everything else that writes to
+    fd 1 (NCCL prints its version banner there, libraries may print warnings) goes to stderr."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real
+
+
 def main():
+    reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
