@@ -463,7 +463,11 @@ class DeviceBatch:
 
     @property
     def n_points(self) -> int:
-        return int(self.data.shape[0])
+        return int(self.data.shape[0]) if self.data is not None else self._n_points
+
+    @property
+    def resident(self) -> bool:
+        return self.data is not None
 
     @classmethod
     def from_host_fields(cls, arrays: Sequence[np.ndarray], chunk: int | None = None) -> "DeviceBatch":
@@ -539,6 +543,8 @@ class DeviceBatch:
             ring.release()
 
     def _np_dtype(self):
+        if self.data is None:
+            return self._host[0].dtype
         return np.dtype(np.float32 if self.data.dtype == _torch().float32 else np.float64)
 
     def to_host_fields(self, chunk: int | None = None) -> np.ndarray:
@@ -547,6 +553,23 @@ class DeviceBatch:
         self._download([host[j] for j in range(self.n_fields)], 0, chunk)
         return host
 
+    def offload(self) -> None:
+        """Move the batch to host memory and free its HBM (used when a FieldList is larger than
+        the device: outputs of finished sub-batches must not pile up in HBM).  From then on
+        `take_column` hands out copies of the host arrays."""
+        if self.data is None:
+            return
+        if self._host is None:
+            self._host = [np.empty((self.n_points,), dtype=self._np_dtype()) for _ in range(self.n_fields)]
+            self._download(self._host)
+        else:  # columns already handed out were the callers'; fetch them again for our own copy
+            missing = [j for j, a in enumerate(self._host) if a is None]
+            for j in missing:
+                self._host[j] = np.empty((self.n_points,), dtype=self._np_dtype())
+                self._download([self._host[j]], first_col=j)
+        self._n_points = self.n_points
+        self.data = None
+
     def take_column(self, col: int) -> np.ndarray:
         """A fresh host array with the values of column `col`, owned by the caller.
 
@@ -554,6 +577,8 @@ class DeviceBatch:
         each array is handed out once without a further copy.  A column asked for again is
         downloaded again (the device copy is the source of truth — callers may mutate what
         they were given, e.g. apply_mask.py:184-185)."""
+        if self.data is None:  # offloaded: the host arrays are the only copy
+            return self._host[col].copy()
         if self._host is None:
             self._host = [np.empty((self.n_points,), dtype=self._np_dtype()) for _ in range(self.n_fields)]
             self._download(self._host)

@@ -297,7 +297,8 @@ def device_column_of(field: Any):
     f = field
     while True:
         if isinstance(f, DeviceColumnField):
-            return f.batch, f.column
+            # an offloaded batch (DeviceBatch.offload) is a host field again
+            return (f.batch, f.column) if getattr(f.batch, "resident", True) else None
         if isinstance(f, NewDataField):
             return None
         if isinstance(f, WrappedField):

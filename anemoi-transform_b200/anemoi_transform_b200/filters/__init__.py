@@ -23,6 +23,7 @@ from .fields import cos_sin_mean_wave_direction as _cos_sin_mwd  # noqa: E402,F4
 from .fields import dewpoint as _dewpoint  # noqa: E402,F401
 from .fields import impute_nans as _impute_nans_fields  # noqa: E402,F401
 from .fields import lnsp_to_sp as _lnsp_to_sp  # noqa: E402,F401
+from .fields import orog_to_z as _orog_to_z  # noqa: E402,F401
 from .fields import q_to_r as _q_to_r  # noqa: E402,F401
 from .fields import regrid as _regrid  # noqa: E402,F401
 from .fields import remove_nans as _remove_nans_fields  # noqa: E402,F401
@@ -57,6 +58,7 @@ def create_filter(context: Any, config: Any):
 _merge_registries()
 
 from . import clip as _clip  # noqa: E402,F401
+from . import geopotential_to_height as _geopotential_to_height  # noqa: E402,F401
 from . import impute_nans as _impute_nans  # noqa: E402,F401
 from . import mask as _mask  # noqa: E402,F401
 from . import remove_nans as _remove_nans  # noqa: E402,F401

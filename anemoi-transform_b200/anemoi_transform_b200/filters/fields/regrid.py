@@ -32,6 +32,12 @@ from . import filter_registry
 LOG = logging.getLogger(__name__)
 
 
+def _free_device_bytes() -> int:
+    torch = require_cuda()
+    free, _ = torch.cuda.mem_get_info()
+    return int(free + torch.cuda.memory_reserved() - torch.cuda.memory_allocated())
+
+
 def as_gridspec(grid: Any) -> dict[str, Any] | None:
     if grid is None:
         return None
@@ -93,7 +99,36 @@ class _BatchedInterpolator:
     def __call__(self, field: Any) -> Any:
         return self.regrid_batch([field])[0]
 
+    #: fraction of the free HBM one sub-batch (inputs + outputs) may take
+    memory_fraction = 0.4
+
     def regrid_batch(self, fields: list[Any]) -> list[Any]:
+        """All fields in one device pass — or, when the FieldList does not fit in HBM, in
+        sub-batches whose outputs are moved to host memory as soon as they are computed."""
+        per_field = self.bytes_per_field(fields[0])
+        limit = max(4, int(self.memory_fraction * _free_device_bytes() // max(1, per_field)) // 4 * 4)
+        if len(fields) <= limit:
+            return self._regrid_resident(fields)
+        LOG.info("regrid: %d fields exceed the device budget (%d per pass): streaming in sub-batches", len(fields), limit)
+        out: list[Any] = []
+        for i in range(0, len(fields), limit):
+            part = self._regrid_resident(fields[i : i + limit])
+            from ...fields import device_column_of
+
+            for batch in {id(b): b for b, _ in filter(None, (device_column_of(f) for f in part))}.values():
+                batch.offload()
+            out.extend(part)
+        return out
+
+    def bytes_per_field(self, field: Any) -> int:
+        """Device bytes one field costs: its input column plus its output column (float64 worst case)."""
+        n_in = int(np.prod(field.shape)) if hasattr(field, "shape") else 0
+        return 8 * (n_in + self.output_points(n_in))
+
+    def output_points(self, n_in: int) -> int:
+        return n_in
+
+    def _regrid_resident(self, fields: list[Any]) -> list[Any]:
         self.prepare(fields[0])
         # numpy dtypes differ per field in principle; batch runs of equal dtype together.
         # Host values are fetched once here (to_numpy decodes / copies) and handed to the upload.
@@ -144,6 +179,9 @@ class MIRMatrix(_BatchedInterpolator):
         self.in_grid = dict(latitudes=loaded["in_latitudes"], longitudes=loaded["in_longitudes"])
         self.out_grid = dict(latitudes=loaded["out_latitudes"], longitudes=loaded["out_longitudes"])
 
+    def output_points(self, n_in: int) -> int:
+        return self.matrix.shape[0]
+
     def apply(self, batch: DeviceBatch) -> DeviceBatch:
         if batch.n_points != self.matrix.shape[1]:
             raise ValueError(f"dimension mismatch: matrix has {self.matrix.shape[1]} columns, field has {batch.n_points} points")
@@ -186,6 +224,9 @@ class ScipyKDTreeNearestNeighbours(_BatchedInterpolator):
                 self.out_grid["longitudes"],
                 _as_device=True,
             )
+
+    def output_points(self, n_in: int) -> int:
+        return int(np.size(self.out_grid["latitudes"]))
 
     def apply(self, batch: DeviceBatch) -> DeviceBatch:
         n_in = (batch.n_points,)

@@ -227,3 +227,46 @@ def test_reference_lnsp_golden_vectors(F):
     assert set(back) == {"lnsp"} and np.allclose(back["lnsp"][0].to_numpy(), LNSP)
     req = F("lnsp_to_sp").patch_data_request({"param": ["sp", "t"]})
     assert req == {"param": ["t", "lnsp"]}
+
+
+def test_reference_orog_to_z_golden_vectors(F):
+    # reference tests/field_filters/test_orog_to_z.py:25-27, 42-78
+    OROG = np.array([[243.87788459, 1892.45371246], [427.80215359, 156.92873391], [2167.93458212, 338.15794671]])
+    out = _by_param(F("orog_to_z_fields").forward(_fl([("orog", OROG), ("t", OROG)])))
+    assert set(out) == {"z", "t"}
+    assert np.array_equal(out["z"][0].to_numpy(), OROG * 9.80665)  # float64 in, float64 out, bit-exact
+    back = _by_param(F("z_to_orog").forward(_fl([("z", OROG * 9.80665)])))
+    assert set(back) == {"orog"} and np.array_equal(back["orog"][0].to_numpy(), OROG * 9.80665 / 9.80665)
+    f32 = OROG.astype(np.float32)
+    out = _by_param(F("orog_to_z").forward(_fl([("orog", f32)])))
+    assert np.array_equal(out["z"][0].to_numpy(), f32 * 9.80665) and out["z"][0].to_numpy().dtype == np.float32
+
+
+def test_fieldlist_larger_than_the_device_budget_streams_in_sub_batches(F, cuda, tmp_path):
+    """`regrid` on a FieldList that does not fit the HBM budget: sub-batches, outputs offloaded to
+    host memory, same values as the resident path, fields still usable by the next filter."""
+    from anemoi_transform_b200 import synthetic as syn
+
+    s_lat, s_lon = syn.regular_latlon(5.0)
+    t_lat, t_lon = syn.octahedral(16)
+    d, i, p, shape = syn.bilinear_matrix(5.0, t_lat, t_lon)
+    syn.save_regrid_npz(tmp_path / "m.npz", d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    rng = np.random.default_rng(4)
+    vals = [rng.normal(280, 10, shape[1]).astype(np.float32) for _ in range(23)]
+    fl = ekd.from_source("list-of-dicts", [dict(param="t", levelist=k, values=v, latitudes=s_lat, longitudes=s_lon) for k, v in enumerate(vals)])
+    want = [f.to_numpy(flatten=True) for f in F("regrid", matrix=str(tmp_path / "m.npz")).forward(fl)]
+    flt = F("regrid", matrix=str(tmp_path / "m.npz"))
+    flt.interpolator.memory_fraction = 1e-12  # forces the minimum of 4 fields per pass
+    out = flt.forward(fl)
+    assert len(out) == 23
+    from anemoi_transform_b200.fields import device_column_of
+
+    assert all(device_column_of(f) is None for f in out)  # offloaded: host fields again
+    for f, w, k in zip(out, want, range(23)):
+        assert f.metadata("levelist") == k
+        a, b = f.to_numpy(flatten=True), f.to_numpy(flatten=True)
+        assert np.array_equal(a, w) and np.array_equal(b, w) and a is not b
+    lat, lon = out[7].grid_points()
+    assert np.array_equal(lat, t_lat) and np.array_equal(lon, t_lon)
+    clipped = F("clip", param="t", minimum=275.0).forward(out)
+    assert np.array_equal(clipped[22].to_numpy(flatten=True), np.clip(want[22], 275.0, None))
