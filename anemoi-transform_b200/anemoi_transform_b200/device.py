@@ -386,7 +386,7 @@ def _parallel_copy(pairs) -> None:
         import os
         from concurrent.futures import ThreadPoolExecutor
 
-        _N_COPY_THREADS = max(1, min(8, (len(os.sched_getaffinity(0)) or 2) - 1))
+        _N_COPY_THREADS = int(os.environ.get("AT_B200_COPY_THREADS", 0)) or max(1, min(8, (len(os.sched_getaffinity(0)) or 2) - 1))
         _COPY_THREADS = ThreadPoolExecutor(max_workers=_N_COPY_THREADS, thread_name_prefix="at-copy")
     if len(pairs) < _N_COPY_THREADS:  # few large fields: split them
         parts = -(-_N_COPY_THREADS // len(pairs))

@@ -143,3 +143,22 @@ def test_sharded_entry_points_equal_the_single_gpu_ones(sp, golden_spatial):
     assert np.array_equal(atd.nearest_grid_points(*lam, *o, num_neighbours_to_return=3), sp.nearest_grid_points(*lam, *o, num_neighbours_to_return=3))
     assert np.array_equal(atd.global_on_lam_mask(*lam, *o), g["gol_none"])
     assert np.array_equal(atd.global_on_lam_mask(*lam, *o, distance_km=150.0), g["gol_150km"])
+
+
+def test_global_on_lam_mask_file_feeds_the_masked_regrid(sp, golden_spatial, tmp_path):
+    """make-regrid-file global-on-lam-mask → regrid(mask=…): the file written on the device path
+    selects exactly the points the reference's mask selects."""
+    from anemoi_transform_b200 import ekd
+    from anemoi_transform_b200.filters import create_filter_by_name
+    from anemoi_transform_b200.regrid_files import make_global_on_lam_mask
+
+    g = golden_spatial
+    mask = make_global_on_lam_mask(g["lam_lat"], g["lam_lon"], g["o_lat"], g["o_lon"], str(tmp_path / "gol.npz"), distance_km=150.0)
+    assert np.array_equal(mask, g["gol_150km"]) and np.array_equal(np.load(tmp_path / "gol.npz")["mask"], g["gol_150km"])
+    rng = np.random.default_rng(1)
+    vals = rng.normal(size=g["o_lat"].size).astype(np.float32)
+    fl = ekd.from_source("list-of-dicts", [dict(param="t", levelist=1, values=vals, latitudes=g["o_lat"], longitudes=g["o_lon"])])
+    out = create_filter_by_name("regrid", mask=str(tmp_path / "gol.npz")).forward(fl)
+    assert np.array_equal(out[0].to_numpy(flatten=True), vals[g["gol_150km"]])
+    lat, lon = out[0].grid_points()
+    assert np.array_equal(lat, g["o_lat"][g["gol_150km"]]) and np.array_equal(lon, g["o_lon"][g["gol_150km"]])
