@@ -12,6 +12,7 @@ from typing import Any
 
 from ..registry import Registry
 from .fields import filter_registry as fields_filter_registry
+from .tabular import filter_registry as tabular_filter_registry
 
 filter_registry = Registry(__name__, entry_point_group="anemoi.transform.filters")
 
@@ -30,10 +31,11 @@ from .fields import remove_nans as _remove_nans_fields  # noqa: E402,F401
 from .fields import rescale as _rescale  # noqa: E402,F401
 from .fields import sum as _sum  # noqa: E402,F401
 from .fields import uv_to_ddff as _uv_to_ddff  # noqa: E402,F401
+from .tabular import assign_to_grid as _assign_to_grid  # noqa: E402,F401
 
 
 def _merge_registries() -> None:
-    for source in (fields_filter_registry,):
+    for source in (fields_filter_registry, tabular_filter_registry):
         for name, factory in source.factories.items():
             try:
                 filter_registry.register(name, factory, aliases=source.aliases().get(name, None))

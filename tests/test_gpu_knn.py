@@ -127,3 +127,24 @@ def test_compact_and_cropping(cuda, golden_spatial):
     assert np.array_equal(got, g["crop_wrap"])
     got = cropping_mask_device(g["g_lat"], g["g_lon"] - 360.0, 10.0, 100.0, -10.0, 140.0).cpu().numpy().astype(bool)
     assert np.array_equal(got, g["crop_plus360"])
+
+
+def test_assign_to_grid_tabular_filter_matches_ckdtree_in_the_plane(cuda):
+    """reference filters/tabular/assign_to_grid.py: nearest grid point of each observation in the
+    flat (lat, lon) plane — distances bitwise cKDTree's, indices equal (random observations do not tie)."""
+    import pandas as pd
+    from scipy.spatial import cKDTree
+
+    from anemoi_transform_b200.filters import create_filter_by_name
+    from anemoi_transform_b200.filters.tabular.assign_to_grid import define_grid
+
+    rng = np.random.default_rng(8)
+    n = 200_000
+    df = pd.DataFrame({"latitude": rng.uniform(-90, 90, n), "longitude": rng.uniform(-180, 180, n), "obsvalue": rng.normal(size=n)})
+    out = create_filter_by_name("assign_to_grid", grid="o48").forward(df)
+    want_d, want_i = cKDTree(define_grid("o48")).query(df[["latitude", "longitude"]])
+    assert list(out.columns) == ["latitude", "longitude", "obsvalue", "grid_index_o48", "distance"]
+    assert np.array_equal(out["distance"].to_numpy(), want_d)
+    assert np.array_equal(out["grid_index_o48"].to_numpy(), want_i)
+    with pytest.raises(ValueError, match="No grid"):
+        create_filter_by_name("assign_to_grid", grid="")
