@@ -13,9 +13,13 @@
 //     and weights, contiguous in memory) is staged in shared memory once per CTA — with a
 //     1-D bulk async copy (TMA, cp.async.bulk + mbarrier) when the matrix has a uniform
 //     row length, so the tile is regular and 16-byte aligned, else with cooperative loads;
-//   - grid.x walks row blocks (fastest) so concurrently resident CTAs reference
-//     neighbouring source rows and the ~2x re-reference of each source row hits L2;
-//     grid.y walks column tiles, bounding the live source working set;
+//   - blockIdx.x = row_block * S + tile_in_supertile: CTAs that are resident together cover S
+//     adjacent column tiles of neighbouring rows (long contiguous spans of each source row,
+//     DRAM page locality) and the ~2x re-reference of each source row hits L2; S is sized from
+//     the matrix's reuse working set; blockIdx.y walks the super-tiles;
+//   - float64 results (float64 matrix and / or fields) run spmm_f64_kernel, same mapping with
+//     16-byte units of X; the pointwise filters run in the epilogue (spmm_fused_kernel) or on
+//     their own (pointwise_kernel), compiled per kind family (epilogue.cuh);
 //   - accumulation is scipy's, bit for bit: sequential in storage order from +0 with
 //     __fmul_rn / __fadd_rn (never contracted to FMA);
 //   - Y is write-once: streaming stores (st.global.cs).
