@@ -6,8 +6,8 @@ What shards:
                              contiguous slice of fields; the CSR matrix is replicated;
                              NO collective on the math path
     kNN / thinning / cutout  queries are independent → sources (and buckets) replicated,
-                             queries split; NCCL all-gather of the int64 indices when every
-                             rank needs the full result
+                             queries split; NCCL all-gather of the int64 indices / uint8
+                             classifications when every rank needs the full result
     global_on_lam_mask       LAM queries split; each rank marks a uint8[n_global] partial mask;
                              all-reduce(MAX) (= bitwise OR on 0/1 bytes), then compaction
     _resolution              self-queries split; all-reduce(MIN) of one float64
@@ -143,3 +143,18 @@ def global_on_lam_mask(lats, lons, global_lats, global_lons, distance_km=None):
     mark = global_index.ball_mark(tuple(a[lo:hi] for a in lam_xyz), distance)
     indices = compact_mask(all_reduce_or(mark)).cpu().numpy()
     return indices if indices.size else np.array(sorted(set()))
+
+
+def cutout_mask(lats, lons, global_lats, global_lons, **kwargs):
+    """`spatial.cutout_mask` with the cropped global points (kNN + triangle classification)
+    sharded over the ranks, uint8 results all-gathered; every rank returns the full mask."""
+    from . import spatial
+
+    return spatial.cutout_mask(lats, lons, global_lats, global_lons, _sharded=True, **kwargs)
+
+
+def thinning_mask(lats, lons, global_lats, global_lons, **kwargs):
+    """`spatial.thinning_mask` with the cropped global points sharded over the ranks."""
+    from . import spatial
+
+    return spatial.thinning_mask(lats, lons, global_lats, global_lons, _sharded=True, **kwargs)

@@ -68,10 +68,32 @@ def _check_latlon_arrays(lats, lons, global_lats, global_lons) -> None:
     assert lats.shape == lons.shape
 
 
-def _resolution(points_xyz) -> float:
-    """min over points of the distance to the 2nd nearest point (spatial.py:93-97)."""
+def _resolution(points_xyz, sharded: bool = False) -> float:
+    """min over points of the distance to the 2nd nearest point (spatial.py:93-97).
+    `sharded`: every rank scans its slice of the points, all-reduce(MIN)."""
     index = points_xyz if isinstance(points_xyz, KnnIndex) else KnnIndex(points_xyz)
-    return index.min_nn_distance()
+    if not sharded:
+        return index.min_nn_distance()
+    from . import distributed as atd
+
+    lo, hi = atd.shard_range(index.n, *atd.world())
+    return atd.all_reduce_min(index.min_nn_distance(lo, hi - lo), device="cuda")
+
+
+def _query_range(n_q: int, sharded: bool) -> tuple[int, int]:
+    if not sharded:
+        return 0, n_q
+    from . import distributed as atd
+
+    return atd.shard_range(n_q, *atd.world())
+
+
+def _gather_queries(local, n_q: int, sharded: bool):
+    if not sharded:
+        return local
+    from . import distributed as atd
+
+    return atd.all_gather_rows(local, n_q)
 
 
 def _distance_km_to_resolution(function: str, distance_km, lam_points, global_points) -> float:
@@ -106,6 +128,7 @@ def cutout_mask(
     min_distance_km: int | float | None = None,
     max_distance_km: int | float | None = None,
     plot: str | None = None,
+    _sharded: bool = False,
 ) -> NDArray[Any]:
     """Mask of the global points to KEEP around a LAM (True = outside the cutout).
 
@@ -139,11 +162,11 @@ def cutout_mask(
     if isinstance(min_distance_km, (int, float)):
         min_distance = min_distance_km / R_earth_km
     elif min_distance_km == "lam":
-        min_distance = _resolution(lam_index)
+        min_distance = _resolution(lam_index, _sharded)
         LOG.info(f"cutout_mask using distance = {min_distance * R_earth_km} km")
     else:
         # None / "global" -> resolution of the (cropped) global points (spatial.py:388-393, 104)
-        min_distance = _resolution(global_xyz) if n_q > 0 else float("inf")
+        min_distance = _resolution(global_xyz, _sharded) if n_q > 0 else float("inf")
         LOG.info(f"cutout_mask using distance = {min_distance * R_earth_km} km")
 
     inside_lam = np.zeros((n_q,), dtype=bool)
@@ -151,20 +174,21 @@ def cutout_mask(
         if neighbours > n_lam:
             # cKDTree pads with index n_lam and the reference then indexes lam_points with it
             raise IndexError(f"index {n_lam} is out of bounds for axis 0 with size {n_lam}")
-        g = tuple(to_device_f64(a) for a in global_xyz)
+        lo, hi = _query_range(n_q, _sharded)  # queries are independent: each rank classifies its slice
+        g = tuple(to_device_f64(a[lo:hi]) for a in global_xyz)
         lam = tuple(to_device_f64(a) for a in lam_xyz)
         idx, dist, _ = lam_index.query(g, k=neighbours)
-        out = torch.empty((n_q,), dtype=torch.uint8, device=idx.device)
+        out = torch.empty((hi - lo,), dtype=torch.uint8, device=idx.device)
         max_distance = -1.0 if max_distance_km is None else max_distance_km / R_earth_km
         call(
             "at_cutout_classify",
             _ptr(lam[0]), _ptr(lam[1]), _ptr(lam[2]), n_lam,
-            _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), n_q,
+            _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), hi - lo,
             _ptr(idx), _ptr(dist), int(neighbours),
             float(min_distance), float(max_distance), int(CUTOUT_DOT_MODE),
             _ptr(out), stream_ptr(),
         )  # fmt: skip
-        inside_lam = out.cpu().numpy().astype(bool)
+        inside_lam = _gather_queries(out, n_q, _sharded).cpu().numpy().astype(bool)
 
     too_far_mask: bool | NDArray[Any] = False
     if isinstance(max_distance_km, (int, float)):
@@ -185,6 +209,7 @@ def thinning_mask(
     global_lats: NDArray[Any],
     global_lons: NDArray[Any],
     cropping_distance: float = 2.0,
+    _sharded: bool = False,
 ) -> NDArray[Any]:
     """Indices of the LAM points closest to each (cropped) global point (spatial.py:443-503)."""
     _check_latlon_arrays(lats, lons, global_lats, global_lons)
@@ -192,8 +217,10 @@ def thinning_mask(
     mask = cropping_mask(global_lats, global_lons, *_crop_box(lats, lons, cropping_distance))
     global_xyz = latlon_to_xyz(global_lats[mask], global_lons[mask])
     index = KnnIndex(latlon_to_xyz(lats, lons))
-    idx, _, _ = index.query(global_xyz, k=1)
-    return idx[:, 0].cpu().numpy()
+    n_q = global_xyz[0].shape[0]
+    lo, hi = _query_range(n_q, _sharded)
+    idx, _, _ = index.query(tuple(a[lo:hi] for a in global_xyz), k=1)
+    return _gather_queries(idx[:, 0].contiguous(), n_q, _sharded).cpu().numpy()
 
 
 def global_on_lam_mask(
