@@ -59,10 +59,10 @@ class _Sym:
 
 
 class _Group:
-    __slots__ = ("kind", "inputs", "outputs")
+    __slots__ = ("kind", "inputs", "outputs", "pa", "pb")
 
-    def __init__(self, kind: int, inputs: list[_Sym], outputs: list[_Sym]):
-        self.kind, self.inputs, self.outputs = kind, inputs, outputs
+    def __init__(self, kind: int, inputs: list[_Sym], outputs: list[_Sym], pa: float = 0.0, pb: float = 0.0):
+        self.kind, self.inputs, self.outputs, self.pa, self.pb = kind, inputs, outputs, pa, pb
 
 
 def _direction(f: Any, cls: type) -> str | None:
@@ -76,9 +76,49 @@ def _direction(f: Any, cls: type) -> str | None:
 def _unwrap(f: Any) -> Any:
     """The field-level implementation behind a dispatcher (`clip`, `mask`)."""
     from .filters.clip import Clip
+    from .filters.geopotential_to_height import GeopotentialToHeight
+    from .filters.impute_nans import ImputeNaNs as ImputeNaNsDispatcher
     from .filters.mask import Mask
 
-    return f.filter if isinstance(f, (Clip, Mask)) else f
+    if isinstance(f, (Clip, Mask)):
+        return f.filter
+    if isinstance(f, (GeopotentialToHeight, ImputeNaNsDispatcher)):
+        return f.field_filter
+    if isinstance(f, ReversedTransform) and isinstance(f.filter, GeopotentialToHeight):
+        return ReversedTransform(f.filter.field_filter)
+    return f
+
+
+def _unary_plan(f: Any):
+    """(filter, direction, kind, pa, pb, metadata) for the one-field-in / one-field-out filters
+    the epilogue runs (`rescale` / `convert`, `lnsp_to_sp`, `impute_nans`, `orog_to_z`), else None.
+    The metadata is what the filter's own `*_transform_batch` attaches to its outputs."""
+    from .constants import g_gravitational_acceleration as g
+    from .filters.fields.impute_nans import ImputeNaNs
+    from .filters.fields.lnsp_to_sp import LnspToSp
+    from .filters.fields.orog_to_z import Orography
+    from .filters.fields.rescale import RescaleMixin
+
+    for cls in (RescaleMixin, LnspToSp, ImputeNaNs, Orography):
+        d = _direction(f, cls)
+        if d is None:
+            continue
+        t = f if isinstance(f, cls) else f.filter
+        fwd = d == "forward"
+        if cls is RescaleMixin:
+            kind = _cabi.EPI_AFFINE if fwd else _cabi.EPI_AFFINE_INV
+            md = dict(param=t.param, units=t.forward_units) if fwd else dict(param=t.param)
+            return t, d, kind, float(t.rescaler.scale), float(t.rescaler.offset), md
+        if cls is LnspToSp:
+            md = {"param": t.surface_pressure, "levelist": None, "level": None} if fwd else {"param": t.log_of_surface_pressure}
+            return t, d, (_cabi.EPI_EXP if fwd else _cabi.EPI_LOG), 0.0, 0.0, md
+        if cls is ImputeNaNs:
+            if not fwd:
+                return None
+            return t, d, _cabi.EPI_IMPUTE_NAN, float(t.value), 0.0, {}
+        md = {"param": t.geopotential} if fwd else {"param": t.orography}
+        return t, d, (_cabi.EPI_AFFINE if fwd else _cabi.EPI_AFFINE_INV), g, 0.0, md
+    return None
 
 
 def is_fusable_follower(f: Any) -> bool:
@@ -88,7 +128,9 @@ def is_fusable_follower(f: Any) -> bool:
     from .filters.fields.uv_to_ddff import WindComponents
 
     f = _unwrap(f)
-    return bool(_direction(f, WindComponents) or _direction(f, HumidityConversion)) or isinstance(f, (Clipper, MaskVariable))
+    if bool(_direction(f, WindComponents) or _direction(f, HumidityConversion)) or isinstance(f, (Clipper, MaskVariable)):
+        return True
+    return _unary_plan(f) is not None
 
 
 def is_fusable_regrid(f: Any) -> bool:
@@ -219,6 +261,18 @@ class FusedRegrid(Filter):
                         s.masked = True
                         md = {"param": f"{s.field.metadata('param')}_{f.rename}"} if f.rename is not None else {}
                         self._retag(s, **md)
+            elif _unary_plan(f) is not None:
+                target, direction, kind, pa, pb, md = _unary_plan(f)
+                selection = target._forward_selection if direction == "forward" else target._backward_selection
+                for pos, sym in enumerate(syms):
+                    if not selection.match(sym.field):
+                        continue
+                    if sym.src[0] != "col" or sym.lo is not None or sym.hi is not None or sym.masked:
+                        raise Unfusable("conversion of a field that was already transformed")
+                    o = sym.transformed(**md)
+                    o.src = ("conv", len(groups), 0)
+                    groups.append(_Group(kind, [sym], [o], pa, pb))
+                    syms[pos] = o
             else:  # pragma: no cover - guarded by is_fusable_follower
                 raise Unfusable(f"unsupported filter {follower}")
 
@@ -279,7 +333,7 @@ class FusedRegrid(Filter):
         # input columns: plain fields first, then the pairs of each conversion kind
         plain = [s for s in syms if s.src[0] == "col"]
         in_fields: list[Any] = [fields[s.inp] for s in plain]
-        segments: list[tuple[int, int, int, int]] = []
+        segments: list[tuple] = []
         out_cols: list[tuple[float, float, float, int]] = []
         assign: list[tuple[_Sym, int]] = []
 
@@ -300,7 +354,26 @@ class FusedRegrid(Filter):
                 assign.append((s, k))
             out_cols = [col_params(s) for s in plain] + [col_params(None)] * (len(in_fields) - len(plain))
         live = set(id(s) for s in syms)
-        for kind in sorted({g.kind for g in groups}):
+        # one-in / one-out kinds: a segment per (kind, constants), columns 1:1
+        unary = [g for g in groups if g.kind not in OUT_PER_PAIR]
+        for key in sorted({(g.kind, g.pa, g.pb) for g in unary}):
+            same = [g for g in unary if (g.kind, g.pa, g.pb) == key]
+            in0, out0 = len(in_fields), round_up(len(out_cols), 4)
+            out_cols += [col_params(None)] * (out0 - len(out_cols))
+            for g in same:
+                if g.inputs[0].inp is None:
+                    raise Unfusable("conversion input that is itself a conversion output")
+                in_fields.append(fields[g.inputs[0].inp])
+            while (len(in_fields) - in0) % 4:
+                in_fields.append(in_fields[-1])
+            seg_out = [col_params(None)] * (len(in_fields) - in0)
+            for k, g in enumerate(same):
+                seg_out[k] = col_params(g.outputs[0])
+                if id(g.outputs[0]) in live:
+                    assign.append((g.outputs[0], out0 + k))
+            segments.append((key[0], in0, len(in_fields) - in0, out0, key[1], key[2]))
+            out_cols += seg_out
+        for kind in sorted({g.kind for g in groups if g.kind in OUT_PER_PAIR}):
             same = [g for g in groups if g.kind == kind]
             in0, out0 = len(in_fields), len(out_cols)
             out0 = round_up(out0, 4)

@@ -51,7 +51,7 @@ N_FIELDS = 3120
 WORKLOAD = "regrid 0.25deg (1440x721=1,038,240 pts) -> N320-shaped (542,080 pts), 4-nnz bilinear CSR, 3120 float32 fields"
 # dram__bytes_read.sum + dram__bytes_write.sum of spmm_f32_kernel per launch on this workload,
 # from the `ncu --set full` capture summarised in profiles/ (None until captured).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 18_983_262_000  # profiles/r01_spmm_ncu.md: 12.237 GB read + 6.746 GB write
+NCU_TRAFFIC_BYTES_PER_LAUNCH = 18_984_274_000  # profiles/r01_spmm_ncu.md: 12.237 GB read + 6.747 GB write
 CPU_SAMPLE_FIELDS = 624  # 1/5 of the workload per CPU step
 
 

@@ -327,6 +327,44 @@ def test_pipeline_fusion_one_launch_same_result(F, golden_regrid, tmp_path):
     _same_fieldlists(fused, _run_unfused(filters, src.forward(None)))
 
 
+def test_pipeline_fusion_of_unary_filters(F, golden_regrid, tmp_path):
+    """`regrid | rescale | orog_to_z | impute_nans | uv_to_ddff | clip | apply_mask` — the one-field
+    filters of SURVEY §8(f) rank 1 fuse into the same single launch, bitwise equal to the chain."""
+    from anemoi_transform_b200.fusion import FusedRegrid
+
+    src, matrix = _fusion_inputs(golden_regrid, tmp_path)
+    filters = [
+        F("regrid", matrix=matrix),
+        F("rescale", param="t", scale=1.8, offset=-459.67),
+        F("z_to_orog", orography="h"),
+        F("impute_nans", param=["q", "z"], value=0.0),
+        F("uv_to_ddff"),
+        F("clip", param="t", maximum=60.0),
+        F("apply_mask", mask_param="lsm", threshold=0.5, threshold_operator=">", param=["h", "ws"]),
+    ]
+    pipe = src
+    for f in filters:
+        pipe = pipe | f
+    plan = pipe.execution_plan()
+    assert len(plan) == 2 and isinstance(plan[1], FusedRegrid)
+    fused = pipe.forward(None)
+    assert plan[1].last_forward_was_fused
+    _same_fieldlists(fused, _run_unfused(filters, src.forward(None)))
+    params = [f.metadata("param") for f in fused]
+    assert "z" not in params and "h" in params and "ws" in params and "lsm" not in params
+    # the reversed forms fuse too; a conversion of a converted field does not, and still agrees
+    filters = [F("regrid", matrix=matrix), F("rescale", param="t", scale=1.8, offset=-459.67).__class__.reversed(param="t", scale=1.8, offset=-459.67), F("sp_to_lnsp", surface_pressure="z")]
+    pipe = src | filters[0] | filters[1] | filters[2]
+    fused = pipe.forward(None)
+    assert pipe.execution_plan()[1].last_forward_was_fused
+    _same_fieldlists(fused, _run_unfused(filters, src.forward(None)))
+    filters = [F("regrid", matrix=matrix), F("rescale", param="t", scale=2.0, offset=1.0), F("rescale", param="t", scale=0.5, offset=0.0)]
+    pipe = src | filters[0] | filters[1] | filters[2]
+    out = pipe.forward(None)
+    assert not pipe.execution_plan()[1].last_forward_was_fused
+    _same_fieldlists(out, _run_unfused(filters, src.forward(None)))
+
+
 def test_pipeline_fusion_falls_back_when_the_epilogue_cannot_express_it(F, golden_regrid, tmp_path):
     src, matrix = _fusion_inputs(golden_regrid, tmp_path)
     # a clip BEFORE the conversion, and two clips of the same field: not expressible, still correct
