@@ -98,6 +98,9 @@ struct SpmmArgs {
     int super;          // column tiles per super-tile: blockIdx.x walks (row block, tile in super-tile)
 };
 
+// (Blackwell's packed mul.rn.f32x2 / add.rn.f32x2 would halve these instructions, but ptxas 12.9
+// contracts the pair into one FFMA2 even with -fmad=false, which breaks bit-exactness with scipy's
+// unfused accumulation; measured gain of the contracted form was 1 % — the kernel is HBM-bound.)
 __device__ __forceinline__ float4 mul_add_rn(float4 acc, float w, float4 x) {
     acc.x = __fadd_rn(acc.x, __fmul_rn(w, x.x));
     acc.y = __fadd_rn(acc.y, __fmul_rn(w, x.y));
