@@ -6,7 +6,7 @@ from typing import Any, Sequence
 
 import numpy as np
 
-from .device import DeviceBatch, gather_cols, require_cuda, round_up
+from .device import DeviceBatch, empty_batch, gather_cols, require_cuda, round_up
 from .fields import device_column_of
 
 
@@ -30,7 +30,7 @@ def fields_to_batch(fields: Sequence[Any], host_values: Sequence[Any] | None = N
             return DeviceBatch(first_batch.data[:, c0 : c0 + round_up(n, 4)], n)
         dtypes = {c[0].data.dtype for c in cols}
         if len(dtypes) == 1 and len({c[0].n_points for c in cols}) == 1:
-            out = torch.zeros((first_batch.n_points, round_up(n, 4)), dtype=first_batch.data.dtype, device=first_batch.data.device)
+            out = empty_batch(first_batch.n_points, n, first_batch.data.dtype, first_batch.data.device)
             # one column-gather launch per source batch, each writing its own output columns
             by_batch: dict[int, list[tuple[int, int]]] = {}
             for j, (b, c) in enumerate(cols):

@@ -55,6 +55,18 @@ def round_up(n: int, m: int) -> int:
     return (n + m - 1) // m * m
 
 
+def empty_batch(n_rows: int, n_cols: int, dtype, device, written: int | None = None):
+    """[n_rows, round_up(n_cols, 4)] without a full memset: the kernels write every real column;
+    only the (at most 3) padding columns, or whatever lies beyond `written`, are zeroed."""
+    torch = _torch()
+    ld = round_up(n_cols, 4)
+    out = torch.empty((n_rows, ld), dtype=dtype, device=device)
+    first_unwritten = n_cols if written is None else written
+    if first_unwritten < ld:
+        out[:, first_unwritten:].zero_()
+    return out
+
+
 class CsrMatrix:
     """A CSR interpolation matrix staged once in HBM (reference: MIRMatrix.__init__,
     filters/fields/regrid.py:281-285)."""
@@ -187,7 +199,7 @@ class Epilogue:
         """Y = epilogue(X) on a resident point-major batch."""
         torch = _torch()
         if out is None:
-            out = torch.zeros((X.shape[0], round_up(self.n_out_cols, 4)), dtype=X.dtype, device=X.device)
+            out = empty_batch(X.shape[0], self.n_out_cols, X.dtype, X.device)
         code = {torch.float32: AT_F32, torch.float64: AT_F64}[X.dtype]
         call("at_pointwise", self.handle, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, _ptr(row_mask), stream_ptr())
         return out
@@ -196,7 +208,7 @@ class Epilogue:
         """Y = epilogue(A · X)."""
         torch = _torch()
         if out is None:
-            out = torch.zeros((csr.shape[0], round_up(self.n_out_cols, 4)), dtype=torch.float32, device=X.device)
+            out = empty_batch(csr.shape[0], self.n_out_cols, torch.float32, X.device)
         call("at_spmm_fused", csr.handle, self.handle, _ptr(X), X.stride(0), _ptr(out), out.stride(0), _ptr(row_mask), stream_ptr())
         return out
 
@@ -305,7 +317,10 @@ def gather_rows(X, idx, n_fields: int | None = None, out=None):
     n_out = int(idx.shape[0])
     n_fields = X.shape[1] if n_fields is None else n_fields
     if out is None:
-        out = torch.zeros((n_out, X.shape[1]), dtype=X.dtype, device=X.device)
+        # whole 16-byte chunks are copied, padding columns included, when the layout allows it
+        per16 = 16 // X.element_size()
+        vec16 = X.stride(0) % per16 == 0
+        out = empty_batch(n_out, X.shape[1], X.dtype, X.device, written=min(X.shape[1], round_up(n_fields, per16)) if vec16 else n_fields)
     err = torch.zeros((1,), dtype=torch.int32, device=X.device)
     call("at_gather_rows", _ptr(idx), n_out, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), n_fields, X.element_size(), _ptr(err), stream_ptr())
     if int(err.item()) != 0:
@@ -320,7 +335,7 @@ def gather_cols(X, cols: Sequence[int], out=None):
     if any(c < 0 or c >= X.shape[1] for c in cols):
         raise IndexError("column index out of range")
     if out is None:
-        out = torch.zeros((X.shape[0], round_up(n_out, 4)), dtype=X.dtype, device=X.device)
+        out = empty_batch(X.shape[0], n_out, X.dtype, X.device)
     index = torch.tensor(list(cols), dtype=torch.int32, device=X.device)
     call("at_gather_cols", _ptr(index), n_out, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), X.element_size(), stream_ptr())
     return out
@@ -332,7 +347,7 @@ def sum_cols(X, cols: Sequence[int], n_groups: int, n_terms: int, out=None):
     if len(cols) != n_groups * n_terms or any(c < 0 or c >= X.shape[1] for c in cols):
         raise IndexError("sum_cols: bad column list")
     if out is None:
-        out = torch.zeros((X.shape[0], round_up(n_groups, 4)), dtype=X.dtype, device=X.device)
+        out = empty_batch(X.shape[0], n_groups, X.dtype, X.device)
     index = torch.tensor(list(cols), dtype=torch.int32, device=X.device)
     code = AT_F32 if X.dtype == torch.float32 else AT_F64
     call("at_sum_cols", _ptr(index), n_groups, n_terms, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, stream_ptr())
@@ -491,7 +506,7 @@ class DeviceBatch:
             if v.size != n_points:
                 raise ValueError(f"field {i} has {v.size} points, expected {n_points}")
         ld = round_up(n_fields, 4)
-        pm = torch.zeros((n_points, ld), dtype=tdtype, device="cuda")
+        pm = empty_batch(n_points, n_fields, tdtype, "cuda")
         chunk = _chunk_fields(n_fields, n_points * dtype.itemsize, chunk)
         ring = _staging_ring(chunk * n_points * dtype.itemsize)
         pins = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.pinned]
