@@ -80,16 +80,21 @@ def build_workload():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).
+
+    nvidia-smi takes ~100 ms to produce its first row, longer than a 20-step timed region, so the
+    sampler is started before the warm-up and `mark()` brackets the timed region: only rows that
+    arrived between the two marks (plus the first one after) are reported."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+    def __init__(self, gpu_index: int, period_ms: int = 10):
+        self.rows, self.proc, self.gpu, self.period_ms = [], None, gpu_index, period_ms
+        self.marks: list[int] = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.period_ms), "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception as e:  # nvidia-smi missing: report that rather than fail the bench
             log("clock sampler unavailable:", e)
@@ -99,16 +104,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def wait_for_first_row(self, timeout_s: float = 5.0):
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        self.marks.append(len(self.rows))
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        time.sleep(0.15)
+        time.sleep(3 * self.period_ms / 1000.0)
         self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        lo, hi = (self.marks + [0, len(self.rows)])[:2] if len(self.marks) >= 2 else (0, len(self.rows))
+        rows = self.rows[max(0, lo - 1) : hi + 1] or self.rows
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in rows if len(r) >= 9 for n, v in zip(names, r[5:9]) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "period_ms": self.period_ms}
 
 
 def bind_to_gpu_numa_node(local_rank: int):
@@ -253,18 +268,24 @@ def run_gpu(args):
         X[:, c0 : c0 + 260] = torch.randn((n_src, min(260, N_FIELDS - c0)), device=dev, dtype=torch.float32, generator=gen) * 15.0 + 280.0
     Y = torch.empty((n_tgt, N_FIELDS), device=dev, dtype=torch.float32)
 
-    for _ in range(args.warmup):
-        csr.apply(X, out=Y, variant=args.variant)
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        csr.apply(X, out=Y, variant=args.variant)
+    if rank == 0:
+        sampler.wait_for_first_row()
+    barrier()
+    if rank == 0:
+        sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         csr.apply(X, out=Y, variant=args.variant)
     ev1.record()
     barrier()
+    if rank == 0:
+        sampler.mark()
     clocks = sampler.stop() if rank == 0 else None
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
