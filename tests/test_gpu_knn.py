@@ -148,3 +148,37 @@ def test_assign_to_grid_tabular_filter_matches_ckdtree_in_the_plane(cuda):
     assert np.array_equal(out["grid_index_o48"].to_numpy(), want_i)
     with pytest.raises(ValueError, match="No grid"):
         create_filter_by_name("assign_to_grid", grid="")
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_point_clouds_against_ckdtree(cuda, seed):
+    """Fuzz the bucketed search on distributions its cell-size estimate was not designed for:
+    points on the sphere, in a plane, on a line, in tight clusters with empty space between,
+    with duplicates, tiny sets; k from 1 to 16, with and without a distance bound.  Distances are
+    bitwise cKDTree's; indices agree wherever d² is not exactly tied."""
+    rng = np.random.default_rng(2000 + seed)
+    n_s, n_q = int(rng.choice([1, 2, 17, 300, 5000, 60000])), int(rng.choice([1, 33, 2000, 40000]))
+    kind = ["sphere", "plane", "line", "clusters", "duplicates", "ball"][seed % 6]
+
+    def cloud(n):
+        if kind == "sphere":
+            p = rng.normal(size=(n, 3))
+            return p / np.linalg.norm(p, axis=1, keepdims=True)
+        if kind == "plane":
+            return np.column_stack([rng.uniform(-90, 90, n), rng.uniform(-180, 180, n), np.zeros(n)])
+        if kind == "line":
+            return np.column_stack([rng.uniform(-1, 1, n), np.full(n, 0.25), np.full(n, -0.5)])
+        if kind == "clusters":
+            centres = rng.normal(size=(5, 3))
+            return centres[rng.integers(0, 5, n)] + rng.normal(scale=1e-4, size=(n, 3))
+        if kind == "duplicates":
+            base = rng.normal(size=(max(1, n // 4), 3))
+            return base[rng.integers(0, base.shape[0], n)]
+        return rng.uniform(-1, 1, size=(n, 3))
+
+    src, tgt = cloud(n_s), cloud(n_q)
+    if kind == "clusters":
+        tgt[: n_q // 2] = rng.uniform(-3, 3, size=(n_q // 2, 3))  # half the queries far from every cluster
+    k = int(min(rng.choice([1, 2, 5, 16]), max(1, n_s)))
+    ub = np.inf if seed % 3 else float(np.median(cKDTree(src).query(tgt, k=1)[0])) or np.inf
+    _check_knn(cuda, tuple(np.ascontiguousarray(src[:, j]) for j in range(3)), tuple(np.ascontiguousarray(tgt[:, j]) for j in range(3)), k, ub)
