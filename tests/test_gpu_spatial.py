@@ -162,3 +162,29 @@ def test_global_on_lam_mask_file_feeds_the_masked_regrid(sp, golden_spatial, tmp
     assert np.array_equal(out[0].to_numpy(flatten=True), vals[g["gol_150km"]])
     lat, lon = out[0].grid_points()
     assert np.array_equal(lat, g["o_lat"][g["gol_150km"]]) and np.array_equal(lon, g["o_lon"][g["gol_150km"]])
+
+
+def test_locally_built_knn_matrix_feeds_the_regrid_filter(sp, tmp_path):
+    """regrid_files.make_knn_matrix: k = 1 is nearest-neighbour regridding as a matrix (same values
+    as `regrid(method="nearest")`, up to the sign of zero); k = 4 rows are convex weights."""
+    from anemoi_transform_b200 import ekd
+    from anemoi_transform_b200.filters import create_filter_by_name
+    from anemoi_transform_b200.regrid_files import make_knn_matrix
+
+    s_lat, s_lon = syn.regular_latlon(2.0)
+    t_lat, t_lon = syn.octahedral(24)
+    rng = np.random.default_rng(5)
+    vals = [rng.normal(280, 10, s_lat.size).astype(np.float32) for _ in range(5)]
+    fl = ekd.from_source("list-of-dicts", [dict(param="t", levelist=k, values=v, latitudes=s_lat, longitudes=s_lon) for k, v in enumerate(vals)])
+    make_knn_matrix(s_lat, s_lon, t_lat, t_lon, str(tmp_path / "nn.npz"), k=1)
+    via_matrix = create_filter_by_name("regrid", matrix=str(tmp_path / "nn.npz")).forward(fl)
+    via_gather = create_filter_by_name("regrid", method="nearest", in_grid=dict(latitudes=s_lat, longitudes=s_lon), out_grid=dict(latitudes=t_lat, longitudes=t_lon)).forward(fl)
+    for a, b in zip(via_matrix, via_gather):
+        assert np.array_equal(a.to_numpy(flatten=True), b.to_numpy(flatten=True))
+    d, i, p, shape = make_knn_matrix(s_lat, s_lon, t_lat, t_lon, k=4, power=2.0)
+    assert shape == (t_lat.size, s_lat.size) and d.dtype == np.float32 and i.dtype == np.int32
+    w = d.reshape(-1, 4)
+    assert np.all(w >= 0) and np.allclose(w.sum(axis=1), 1.0, atol=1e-6) and np.all(np.diff(i.reshape(-1, 4), axis=1) > 0)
+    on_source = np.nonzero((np.isin(t_lat, s_lat)) & (np.isin(t_lon, s_lon)))[0]
+    for r in on_source[:5]:  # a target on a source point takes that source alone
+        assert np.sort(w[r])[-1] == 1.0
