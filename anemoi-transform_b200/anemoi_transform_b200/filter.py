@@ -5,7 +5,6 @@ from __future__ import annotations
 
 import logging
 from abc import abstractmethod
-from functools import singledispatchmethod
 from typing import Any, Callable
 
 import numpy as np
@@ -46,20 +45,29 @@ class DispatchingFilter(Transform):
             if overridden(f"backward_{kind}") and not overridden(f"forward_{kind}"):
                 raise TypeError(f"{cls.__name__} overrides `backward_{kind}` but not `forward_{kind}`")
 
-    @singledispatchmethod
+    def _route(self, direction: str, data: Any) -> Any:
+        """Pick `<direction>_fields` for FieldLists, `<direction>_tabular` for DataFrames and the
+        direction's fallback (which raises) for anything else."""
+        if isinstance(data, ekd.FieldList):
+            kind = "fields"
+        elif isinstance(data, _DataFrame):
+            kind = "tabular"
+        else:
+            kind = "fallback"
+        return getattr(self, f"{direction}_{kind}")(data)
+
     def forward(self, data: Any) -> Any:
-        return self.forward_fallback(data)
+        return self._route("forward", data)
 
-    @forward.register
-    def _(self, data: ekd.FieldList) -> Any:
-        return self.forward_fields(data)
+    def backward(self, data: Any) -> Any:
+        return self._route("backward", data)
 
-    @forward.register
-    def _(self, data: _DataFrame) -> Any:
-        return self.forward_tabular(data)
-
+    # defaults: a kind a subclass does not implement ends in the direction's fallback
     def forward_fallback(self, data: Any) -> Any:
         raise TypeError(f"No forward method for {type(data)}")
+
+    def backward_fallback(self, data: Any) -> Any:
+        raise NotImplementedError(f"No backward method for {type(data)}")
 
     def forward_fields(self, data: Any) -> Any:
         return self.forward_fallback(data)
@@ -67,25 +75,10 @@ class DispatchingFilter(Transform):
     def forward_tabular(self, data: Any) -> Any:
         return self.forward_fallback(data)
 
-    @singledispatchmethod
-    def backward(self, data: Any) -> Any:
+    def backward_fields(self, data: Any) -> Any:
         return self.backward_fallback(data)
-
-    @backward.register
-    def _(self, data: ekd.FieldList) -> Any:
-        return self.backward_fields(data)
-
-    @backward.register
-    def _(self, data: _DataFrame) -> Any:
-        return self.backward_tabular(data)
-
-    def backward_fallback(self, data: Any) -> Any:
-        raise NotImplementedError(f"No backward method for {type(data)}")
 
     def backward_tabular(self, data: Any) -> Any:
-        return self.backward_fallback(data)
-
-    def backward_fields(self, data: Any) -> Any:
         return self.backward_fallback(data)
 
 

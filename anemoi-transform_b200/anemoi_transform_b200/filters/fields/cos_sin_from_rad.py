@@ -16,6 +16,7 @@ from ...batching import fields_to_batch
 from ...device import range_flags
 from ...matching import MatchingFieldsFilter, MatchingSpec
 from . import filter_registry
+from ._requests import replace_products
 from .pointwise import NO_COL, device_field, run_epilogue
 
 
@@ -65,10 +66,4 @@ class CosSinFromRad(MatchingFieldsFilter):
         return [[device_field(out, i, g["cos_param"], param=self.param)] for i, g in enumerate(groups)]
 
     def patch_data_request(self, data_request: dict[str, Any]) -> dict[str, Any]:
-        param = data_request.get("param")
-        if param is None:
-            return data_request
-        if self.cos_param in param or self.sin_param in param:
-            data_request["param"] = [p for p in param if p not in (self.cos_param, self.sin_param)]
-            data_request["param"].append(self.param)
-        return data_request
+        return replace_products(data_request, (self.cos_param, self.sin_param), self.param)

@@ -14,6 +14,7 @@ from ... import _cabi
 from ...batching import fields_to_batch
 from ...matching import MatchingFieldsFilter, MatchingSpec
 from . import filter_registry
+from ._requests import replace_products
 from .pointwise import NO_COL, device_field, run_epilogue
 
 
@@ -65,10 +66,4 @@ class CosSinWaveDirection(MatchingFieldsFilter):
         return [[device_field(out, i, g["cos_mean_wave_direction"], param=self.mean_wave_direction)] for i, g in enumerate(groups)]
 
     def patch_data_request(self, data_request: dict[str, Any]) -> dict[str, Any]:
-        param = data_request.get("param")
-        if param is None:
-            return data_request
-        if self.cos_mean_wave_direction in param or self.sin_mean_wave_direction in param:
-            data_request["param"] = [p for p in param if p not in (self.cos_mean_wave_direction, self.sin_mean_wave_direction)]
-            data_request["param"].append(self.mean_wave_direction)
-        return data_request
+        return replace_products(data_request, (self.cos_mean_wave_direction, self.sin_mean_wave_direction), self.mean_wave_direction)

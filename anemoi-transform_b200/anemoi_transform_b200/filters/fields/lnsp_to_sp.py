@@ -10,6 +10,7 @@ from typing import Any
 from ... import _cabi
 from ...filter import SingleFieldFilter
 from . import filter_registry
+from ._requests import swap_param
 from .pointwise import NO_COL, device_field, run_epilogue
 
 
@@ -40,19 +41,12 @@ class LnspToSp(SingleFieldFilter):
         return [device_field(out, i, f, param=self.log_of_surface_pressure) for i, f in enumerate(fields)]
 
     def patch_data_request(self, data_request: dict[str, Any]) -> dict[str, Any]:
-        param = data_request.get("param")
-        if param is None:
-            return data_request
-        param = param if isinstance(param, list) else [param]
-        if self.surface_pressure in param and self.log_of_surface_pressure in param:
-            raise ValueError("Data request cannot contain both surface pressure and log of surface pressure parameters.")
-        if self.surface_pressure in param:
-            data_request["param"].remove(self.surface_pressure)
-            data_request["param"].append(self.log_of_surface_pressure)
-        elif self.log_of_surface_pressure in param:
-            data_request["param"].remove(self.log_of_surface_pressure)
-            data_request["param"].append(self.surface_pressure)
-        return data_request
+        return swap_param(
+            data_request,
+            self.surface_pressure,
+            self.log_of_surface_pressure,
+            "Data request cannot contain both surface pressure and log of surface pressure parameters.",
+        )
 
 
 filter_registry.register("lnsp_to_sp", LnspToSp)

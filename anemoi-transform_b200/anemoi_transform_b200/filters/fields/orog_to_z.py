@@ -13,6 +13,7 @@ from ... import _cabi
 from ...constants import g_gravitational_acceleration
 from ...filter import SingleFieldFilter
 from . import filter_registry
+from ._requests import rename_on_levels
 from .pointwise import NO_COL, device_field, run_epilogue
 
 
@@ -42,17 +43,7 @@ class Orography(SingleFieldFilter):
         return [device_field(out, i, f, param=self.orography) for i, f in enumerate(fields)]
 
     def patch_data_request(self, data_request: Any) -> Any:
-        param = data_request.get("param")
-        if param is None:
-            return data_request
-        param = param if isinstance(param, list) else [param]
-        if self.geopotential in param and self.orography in param:
-            raise ValueError("Data request cannot contain both orography and geopotential parameters.")
-        if self.geopotential in param and (data_request.get("levtype", "") == "pl" or data_request.get("levelist", [])):
-            data_request["param"] = [self.orography if p == self.geopotential else p for p in param]
-        elif self.orography in param and (data_request.get("levtype", "") == "pl" or data_request.get("levelist", [])):
-            data_request["param"] = [self.geopotential if p == self.orography else p for p in param]
-        return data_request
+        return rename_on_levels(data_request, self.geopotential, self.orography, "Data request cannot contain both orography and geopotential parameters.")
 
 
 filter_registry.register("orog_to_z_fields", Orography)

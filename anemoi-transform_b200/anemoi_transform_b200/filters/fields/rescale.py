@@ -1,13 +1,13 @@
 """`rescale` / `convert` — reference `filters/fields/rescale.py:19-111`.
 
-`x * scale + offset` forward, `(x - offset) / scale` backward, on every field of the selected
-param in one device pass (kernels: AT_EPI_AFFINE / AT_EPI_AFFINE_INV in csrc/epilogue.cuh —
-multiply then add, never fused, so float32 and float64 results are numpy's bit for bit).
+Forward `x·scale + offset`, backward `(x − offset) / scale`, applied to every field of the
+selected param in one device pass (AT_EPI_AFFINE / AT_EPI_AFFINE_INV in csrc/epilogue.cuh:
+multiply then add, never fused, IEEE division — float32 and float64 results are numpy's bit
+for bit).  `convert` derives scale and offset from two units with pint, like the reference.
 """
 
 from __future__ import annotations
 
-from abc import ABC, abstractmethod
 from typing import Any
 
 from ... import _cabi
@@ -17,11 +17,10 @@ from .pointwise import NO_COL, device_field, run_epilogue
 
 
 class Rescaler:
-    """Host-side statement of the two formulas (reference rescale.py:19-29)."""
+    """The affine map and its inverse as plain Python (what the device kernels compute)."""
 
     def __init__(self, scale: float, offset: float):
-        self.scale = scale
-        self.offset = offset
+        self.scale, self.offset = scale, offset
 
     def forward(self, x):
         return x * self.scale + self.offset
@@ -30,63 +29,61 @@ class Rescaler:
         return (x - self.offset) / self.scale
 
 
-class RescaleMixin(ABC):
-    param: str
+class _AffineFilter(SingleFieldFilter):
+    """Shared device path of `Rescale` and `Convert`; subclasses set `self.rescaler` (and the
+    unit names) in `prepare_filter`."""
+
     rescaler: Rescaler
     forward_units = None
     backward_units = None
 
-    @abstractmethod
-    def prepare_filter(self):
-        raise NotImplementedError("prepare_filter must be implemented by subclasses.")
-
-    def forward_select(self):
+    def forward_select(self) -> dict[str, Any]:
         return {"param": self.param}
 
+    def _run(self, kind: int, fields: list[Any], **metadata: Any) -> list[Any]:
+        pa, pb = float(self.rescaler.scale), float(self.rescaler.offset)
+        out = run_epilogue(kind, fields, [NO_COL] * len(fields), pa=pa, pb=pb)
+        return [device_field(out, i, f, param=self.param, **metadata) for i, f in enumerate(fields)]
+
+    def forward_transform_batch(self, fields: list[Any]) -> list[Any]:
+        return self._run(_cabi.EPI_AFFINE, fields, units=self.forward_units)
+
+    def backward_transform_batch(self, fields: list[Any]) -> list[Any]:
+        return self._run(_cabi.EPI_AFFINE_INV, fields)
+
     def forward_transform(self, param: Any) -> Any:
-        """Apply the forward transformation (x to ax+b)."""
         return self.forward_transform_batch([param])[0]
 
     def backward_transform(self, param: Any) -> Any:
-        """Apply the backward transformation (ax+b to x)."""
         return self.backward_transform_batch([param])[0]
 
-    def forward_transform_batch(self, fields: list[Any]) -> list[Any]:
-        out = run_epilogue(_cabi.EPI_AFFINE, fields, [NO_COL] * len(fields), pa=float(self.rescaler.scale), pb=float(self.rescaler.offset))
-        return [device_field(out, i, f, param=self.param, units=self.forward_units) for i, f in enumerate(fields)]
 
-    def backward_transform_batch(self, fields: list[Any]) -> list[Any]:
-        out = run_epilogue(_cabi.EPI_AFFINE_INV, fields, [NO_COL] * len(fields), pa=float(self.rescaler.scale), pb=float(self.rescaler.offset))
-        return [device_field(out, i, f, param=self.param) for i, f in enumerate(fields)]
+# name kept for code that tests `isinstance(f, RescaleMixin)` (fusion planner)
+RescaleMixin = _AffineFilter
 
 
-class Rescale(RescaleMixin, SingleFieldFilter):
-    """A filter to rescale a parameter from a scale and an offset, and back."""
+class Rescale(_AffineFilter):
+    """Rescale a parameter with a scale and an offset, and back."""
 
     required_inputs = ("scale", "offset", "param")
 
-    def prepare_filter(self):
+    def prepare_filter(self) -> None:
         self.rescaler = Rescaler(self.scale, self.offset)
 
 
-class Convert(RescaleMixin, SingleFieldFilter):
-    """A filter to convert a parameter in a given unit to another unit, and back (uses pint
-    to derive the scale and offset, like the reference: rescale.py:92-106)."""
+class Convert(_AffineFilter):
+    """Convert a parameter from `unit_in` to `unit_out`, and back (needs pint)."""
 
     required_inputs = ("unit_in", "unit_out", "param")
 
-    def prepare_filter(self):
+    def prepare_filter(self) -> None:
         import pint
 
-        ureg = pint.UnitRegistry()
-        self.forward_units = self.unit_out
-        self.backward_units = self.unit_in
-        x1, x2 = 0.0, 1.0
-        y1 = ureg.Quantity(x1, self.unit_in).to(self.unit_out).magnitude
-        y2 = ureg.Quantity(x2, self.unit_in).to(self.unit_out).magnitude
-        scale = (y2 - y1) / (x2 - x1)
-        offset = y1 - scale * x1
-        self.rescaler = Rescaler(scale, offset)
+        quantity = pint.UnitRegistry().Quantity
+        at_zero = quantity(0.0, self.unit_in).to(self.unit_out).magnitude
+        at_one = quantity(1.0, self.unit_in).to(self.unit_out).magnitude
+        self.forward_units, self.backward_units = self.unit_out, self.unit_in
+        self.rescaler = Rescaler(at_one - at_zero, at_zero)
 
 
 filter_registry.register("rescale", Rescale)

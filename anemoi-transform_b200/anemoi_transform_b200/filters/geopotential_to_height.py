@@ -1,5 +1,10 @@
-"""`geopotential_to_height` / `orog_to_z` dispatcher — reference `filters/geopotential_to_height.py:19-56`
-(field branch; the tabular branch stays with the reference implementation)."""
+"""`geopotential_to_height` (alias `orog_to_z`) and `height_to_geopotential` (alias `z_to_orog`)
+— reference `filters/geopotential_to_height.py:19-56`.  Only the field branch is provided; the
+tabular branch stays with the reference implementation.
+
+The two spellings of the height key (`height`, `orography`) are mutually exclusive; the
+geopotential key defaults to "z" and the height key to "orog".
+"""
 
 from __future__ import annotations
 
@@ -7,19 +12,20 @@ from typing import Any
 
 from ..filter import DispatchingFilter
 from . import filter_registry
-from .fields.orog_to_z import Orography as OrographyFields
+from .fields.orog_to_z import Orography
+
+
+def _height_key(config: dict[str, Any]) -> str:
+    if "height" in config and "orography" in config:
+        raise ValueError("Must specify either 'height' or 'orography' parameter, but not both.")
+    return config.get("height", config.get("orography", "orog"))
 
 
 class GeopotentialToHeight(DispatchingFilter):
-    """Convert from geopotential to height for field datasets."""
+    """Orography / height (m) ↔ geopotential (m²/s²) for field datasets."""
 
     def __init__(self, **config: Any) -> None:
-        config["geopotential"] = config.get("geopotential", "z")
-        if ("height" in config) and ("orography" in config):
-            raise ValueError("Must specify either 'height' or 'orography' parameter, but not both.")
-        if "height" not in config:
-            config["height"] = config.pop("orography", "orog")
-        self.field_filter = OrographyFields(geopotential=config["geopotential"], orography=config["height"])
+        self.field_filter = Orography(geopotential=config.get("geopotential", "z"), orography=_height_key(config))
 
     def forward_fields(self, data: Any) -> Any:
         return self.field_filter.forward(data)

@@ -34,6 +34,7 @@ HOT_PATH_MODULES = (
     "anemoi.transform.filters.fields.cos_sin_mean_wave_direction",
     "anemoi.transform.filters.fields.dewpoint",
     "anemoi.transform.filters.fields.sum",
+    "anemoi.transform.filters.fields.orog_to_z",
 )
 
 

@@ -36,3 +36,27 @@ def test_goldens_are_reproducible(ref, golden_spatial):
     sp = ref["spatial"]
     assert np.array_equal(sp.cutout_mask(g["lam_lat"], g["lam_lon"], g["o_lat"], g["o_lon"]), g["cutout_default"])
     assert np.array_equal(sp.nearest_grid_points(g["g_lat"], g["g_lon"], g["o_lat"], g["o_lon"]), g["ngp_k1"])
+
+
+def test_patch_data_request_matches_the_reference_filters(ref):
+    """Host-only behaviour of the product's filters against the reference's classes: the
+    `patch_data_request` rewrites (no GPU involved)."""
+    import copy
+
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    cases = [
+        (F("orog_to_z_fields"), ref["orog_to_z"].Orography() if "orog_to_z" in ref else None,
+         [{"param": ["z", "t"], "levtype": "pl"}, {"param": ["orog", "t"], "levelist": [500]}, {"param": ["z", "t"], "levtype": "sfc"}, {"param": "z", "levtype": "pl"}, {"param": ["q"]}, {}]),
+        (F("lnsp_to_sp"), ref["lnsp_to_sp"].LnspToSp(), [{"param": ["sp", "t"]}, {"param": ["lnsp"]}, {"param": ["q"]}, {}]),
+        (F("cos_sin_from_rad", param="x"), ref["cos_sin_from_rad"].CosSinFromRad(param="x"), [{"param": ["cos_x", "t"]}, {"param": ["sin_x", "cos_x"]}, {"param": ["q"]}, {}]),
+        (F("cos_sin_mean_wave_direction"), ref["cos_sin_mean_wave_direction"].CosSinWaveDirection(), [{"param": ["cos_mwd", "t"]}, {"param": ["mwd"]}, {}]),
+    ]  # fmt: skip
+    for mine, theirs, requests in cases:
+        if theirs is None:
+            continue
+        for req in requests:
+            assert mine.patch_data_request(copy.deepcopy(req)) == theirs.patch_data_request(copy.deepcopy(req)), (type(mine).__name__, req)
+    for both, flt in (({"param": ["sp", "lnsp"]}, F("lnsp_to_sp")), ({"param": ["z", "orog"]}, F("orog_to_z_fields"))):
+        with pytest.raises(ValueError, match="cannot contain both"):
+            flt.patch_data_request(both)
