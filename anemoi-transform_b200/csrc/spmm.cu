@@ -333,8 +333,8 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
 // Warp w of a CTA owns tile-table entry blockIdx.y * 8 + w (32 lanes x 4 input columns, one
 // kind) for all of the CTA's rows: the 8 warps together read 4 KB of contiguous columns per row
 // (DRAM page locality), and everything row-invariant (pressures, clip bounds, mask bits) lives
-// in registers.  Copy-like tiles (clip / mask only) are latency-bound: kPwRows rows of loads in
-// flight.  Transcendental tiles are issue-bound (uv_to_ddff is ~85 instructions per pair against
+// in registers.  Copy-like tiles (clip / mask, affine, impute) are latency-bound: kPwRows
+// rows of loads in flight.  Transcendental tiles are issue-bound (uv_to_ddff is ~85 instructions per pair against
 // ~88 issue slots per 16 bytes at the HBM roofline): one copy of the epilogue code, the next
 // row's load in flight behind it, 4 CTAs per SM.
 constexpr int kPwRows = 4;
@@ -344,17 +344,23 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     const long long r0 = static_cast<long long>(blockIdx.x) * f.rows_per_cta;
     const int nrows = static_cast<int>(min(static_cast<long long>(f.rows_per_cta), f.n_rows - r0));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int t_index = blockIdx.y * kWarps + warp;
-    if (t_index >= f.n_tiles) return;
-    const EpiTile tile = f.tiles[t_index];
+    // A CTA covers up to 8 table entries; when fewer are left (narrow batches) the spare warps
+    // take a share of the rows instead of idling: warp w -> entry w % t_here, row group w / t_here.
+    const int t_here = min(kWarps, f.n_tiles - static_cast<int>(blockIdx.y) * kWarps);
+    const int groups = kWarps / t_here, group = warp / t_here;
+    if (group >= groups) return;
+    const EpiTile tile = f.tiles[blockIdx.y * kWarps + warp % t_here];
     if (lane >= tile.n_vec) return;
     const bool any_mask = f.row_mask != nullptr && (tile.flags_any & AT_COL_MASK) != 0;
     const T* xcol = f.X + 4 * static_cast<size_t>(tile.in_vec0 + lane);
     const EpiClip<T> clip = epilogue_prepare_clip<T>(tile, lane, f.cols);
 
-    if (tile.kind == AT_EPI_PLAIN) {
-        T* ycol = f.Y + tile.out_col0 + 4 * lane;
-        for (int lr = 0; lr < nrows; lr += kPwRows) {
+    // one-in / one-out kinds with next to no arithmetic (clip / mask only, affine, impute) are
+    // latency-bound copies: kPwRows rows of loads in flight, the small switch inlined once per row
+    constexpr uint32_t kCopyLike = kind_bit(AT_EPI_PLAIN) | kind_bit(AT_EPI_AFFINE) | kind_bit(AT_EPI_AFFINE_INV) | kind_bit(AT_EPI_IMPUTE_NAN);
+    if ((kind_bit(tile.kind) & kCopyLike) != 0) {
+        const EpiLane<T> none = {T(0), T(0)};
+        for (int lr = group * kPwRows; lr < nrows; lr += groups * kPwRows) {
             T a[kPwRows][4];
             bool masked[kPwRows];
 #pragma unroll
@@ -367,27 +373,27 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
             }
 #pragma unroll
             for (int j = 0; j < kPwRows; ++j)
-                if (lr + j < nrows) {
-                    if (tile.flags_any != 0) clip_mask_n<T, 4, true>(a[j], 0, f.cols, &clip, masked[j]);
-                    store4(ycol + static_cast<size_t>(r0 + lr + j) * f.ldy, a[j][0], a[j][1], a[j][2], a[j][3]);
-                }
+                if (lr + j < nrows)
+                    epilogue_store<T, true, FAM & kCopyLike>(tile, lane, a[j][0], a[j][1], a[j][2], a[j][3], none, f.cols, masked[j],
+                                                            f.Y + static_cast<size_t>(r0 + lr + j) * f.ldy, &clip);
         }
         return;
     }
 
     const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
+    if (group >= nrows) return;
     T n0, n1, n2, n3;
     bool nmask = false;
-    load4(xcol + static_cast<size_t>(r0) * f.ldx, n0, n1, n2, n3);
-    if (any_mask) nmask = f.row_mask[r0] != 0;
+    load4(xcol + static_cast<size_t>(r0 + group) * f.ldx, n0, n1, n2, n3);
+    if (any_mask) nmask = f.row_mask[r0 + group] != 0;
 #pragma unroll 1
-    for (int lr = 0; lr < nrows; ++lr) {
+    for (int lr = group; lr < nrows; lr += groups) {
         const long long row = r0 + lr;
         const T a0 = n0, a1 = n1, a2 = n2, a3 = n3;
         const bool masked = nmask;
-        if (lr + 1 < nrows) {
-            load4(xcol + static_cast<size_t>(row + 1) * f.ldx, n0, n1, n2, n3);
-            if (any_mask) nmask = f.row_mask[row + 1] != 0;
+        if (lr + groups < nrows) {
+            load4(xcol + static_cast<size_t>(row + groups) * f.ldx, n0, n1, n2, n3);
+            if (any_mask) nmask = f.row_mask[row + groups] != 0;
         }
         epilogue_store<T, true, FAM>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
     }
