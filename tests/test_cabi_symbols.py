@@ -46,3 +46,48 @@ def test_every_entry_point_cites_the_reference():
     text = (REPO / "include" / "at_b200.h").read_text()
     for ref in ("regrid.py:309-310", "regrid.py:281-285", "spatial.py:236-275", "spatial.py:189-233", "spatial.py:533-534", "spatial.py:93-97", "apply_mask.py:160-163", "regrid.py:380"):
         assert ref in text, ref
+
+
+def test_a_plain_c_program_can_consume_the_header_and_the_library(native_library, tmp_path):
+    """The boundary is a C ABI: a C99 translation unit includes include/at_b200.h, links
+    libat_b200.so and calls it (host-only entry points here; argument validation must answer
+    with a status and a message, never crash)."""
+    import shutil
+    import subprocess
+
+    from anemoi_transform_b200 import _cabi
+
+    if shutil.which("gcc") is None:
+        import pytest
+
+        pytest.skip("gcc not available")
+    lib = _cabi.library_path()
+    src = tmp_path / "consumer.c"
+    src.write_text(
+        """
+#include <stdio.h>
+#include <string.h>
+#include "at_b200.h"
+int main(void) {
+    at_csr_t* csr = NULL;
+    int32_t indptr[2] = {0, 1};
+    int32_t indices[1] = {7}; /* column 7 of a 1 x 3 matrix: invalid */
+    float data[1] = {1.0f};
+    int rc;
+    if (at_version() < 100) return 1;
+    rc = at_csr_create(1, 3, 1, indptr, AT_I32, indices, AT_I32, data, AT_F32, &csr);
+    if (rc != AT_ERR_INVALID || csr != NULL) return 2;
+    if (strstr(at_last_error(), "indices") == NULL) return 3;
+    if (at_spmm(NULL, NULL, AT_F32, 0, NULL, AT_F32, 0, 0, 0, NULL) == AT_OK) return 4;
+    if (at_csr_destroy(NULL) != AT_OK || at_knn_destroy(NULL) != AT_OK || at_pipeline_destroy(NULL) != AT_OK) return 5;
+    printf("consumer ok: %s\\n", at_last_error());
+    return 0;
+}
+"""
+    )
+    exe = tmp_path / "consumer"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", f"-I{REPO / 'include'}", str(src), "-o", str(exe), str(lib), f"-Wl,-rpath,{lib.parent}"]
+    build = subprocess.run(cmd, capture_output=True, text=True)
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and "consumer ok" in run.stdout, (run.returncode, run.stdout, run.stderr)
