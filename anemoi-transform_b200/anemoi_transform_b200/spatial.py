@@ -48,14 +48,63 @@ def xyz_to_latlon(x: NDArray[Any], y: NDArray[Any], z: NDArray[Any]) -> tuple[ND
     )
 
 
-def latlon_to_xyz(lat: NDArray[Any], lon: NDArray[Any], radius: float = 1.0) -> tuple[NDArray[Any], NDArray[Any], NDArray[Any]]:
-    """Latitude, longitude in degrees → Cartesian coordinates on a sphere (spatial.py:132-167)."""
+def _latlon_to_xyz_serial(lat, lon, radius):
     phi = np.deg2rad(lat)
     lda = np.deg2rad(lon)
     cos_phi = np.cos(phi)
     x = cos_phi * np.cos(lda) * radius
     y = cos_phi * np.sin(lda) * radius
     z = np.sin(phi) * radius
+    return x, y, z
+
+
+_THREADED_TRIG_OK: bool | None = None
+_TRIG_THREADS = None
+
+
+def _threaded_trig_is_exact() -> bool:
+    """numpy's ufuncs are elementwise, but their SIMD kernels treat array tails separately; check
+    once per process that evaluating in slices gives the very same bits as one call, so the
+    threaded path can never change a nearest-neighbour index."""
+    global _THREADED_TRIG_OK
+    if _THREADED_TRIG_OK is None:
+        rng = np.random.default_rng(12345)
+        lat, lon = rng.uniform(-90, 90, 20011), rng.uniform(-360, 720, 20011)
+        whole = _latlon_to_xyz_serial(lat, lon, 1.0)
+        cuts = [0, 1, 4, 9, 1000, 1003, 7777, 12345, 20011]
+        parts = [_latlon_to_xyz_serial(lat[a:b], lon[a:b], 1.0) for a, b in zip(cuts[:-1], cuts[1:])]
+        _THREADED_TRIG_OK = all(np.array_equal(np.concatenate([p[k] for p in parts]).view(np.uint64), whole[k].view(np.uint64)) for k in range(3))
+    return _THREADED_TRIG_OK
+
+
+def latlon_to_xyz(lat: NDArray[Any], lon: NDArray[Any], radius: float = 1.0) -> tuple[NDArray[Any], NDArray[Any], NDArray[Any]]:
+    """Latitude, longitude in degrees → Cartesian coordinates on a sphere (spatial.py:132-167).
+
+    numpy on the host, on purpose (module docstring).  Large inputs are evaluated in slices on a
+    few host threads (numpy releases the GIL inside ufuncs) — the same numpy calls on the same
+    elements, bit-identical to one call (verified once per process), several times faster for
+    the millions of points of a global grid."""
+    global _TRIG_THREADS
+    lat_a, lon_a = np.asarray(lat), np.asarray(lon)
+    n = lat_a.size
+    if n < 500_000 or lat_a.ndim != 1 or lon_a.shape != lat_a.shape or lat_a.dtype != np.float64 or lon_a.dtype != np.float64 or not _threaded_trig_is_exact():
+        return _latlon_to_xyz_serial(lat, lon, radius)
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    workers = max(1, min(8, (len(os.sched_getaffinity(0)) or 2) - 1))
+    if workers == 1:
+        return _latlon_to_xyz_serial(lat, lon, radius)
+    if _TRIG_THREADS is None:
+        _TRIG_THREADS = ThreadPoolExecutor(max_workers=workers, thread_name_prefix="at-trig")
+    x, y, z = (np.empty(n, dtype=np.float64) for _ in range(3))
+    cuts = np.linspace(0, n, 4 * workers + 1).astype(np.int64)
+
+    def work(ab):
+        a, b = ab
+        x[a:b], y[a:b], z[a:b] = _latlon_to_xyz_serial(lat_a[a:b], lon_a[a:b], radius)
+
+    list(_TRIG_THREADS.map(work, zip(cuts[:-1], cuts[1:])))
     return x, y, z
 
 
