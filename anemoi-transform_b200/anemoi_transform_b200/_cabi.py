@@ -85,6 +85,7 @@ PROTOTYPES = {
     "at_min_nn_distance": (c_int, [c_void_p, c_int64, c_int64, POINTER(c_double), c_void_p]),
     "at_compact_mask": (c_int, [c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p]),
     "at_cropping_mask": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double, c_void_p, c_void_p]),
+    "at_outline_classify": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "at_cutout_classify": (
         c_int,
         [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_void_p, c_void_p],

@@ -297,6 +297,29 @@ def global_on_lam_mask(
     return indices
 
 
+def outline(lats: NDArray[Any], lons: NDArray[Any], neighbours: int = 5) -> list[int]:
+    """Indices of the outline points of a grid (spatial.py:539-584): the points that are not
+    inside any triangle of the fan spanned by their own nearest neighbours.
+
+    The fan is built from the neighbours in cKDTree's order; where several neighbours are at
+    exactly the same float64 distance (regular grids) that order is cKDTree's traversal order
+    and this implementation's is (distance, index) — the module's tie policy — so on such grids
+    the outline can differ from the reference's in the tied points."""
+    torch = require_cuda()
+    xyz = latlon_to_xyz(lats, lons)
+    n = int(xyz[0].shape[0])
+    if n == 0:
+        return []
+    if neighbours > n:
+        raise IndexError(f"index {n} is out of bounds for axis 0 with size {n}")
+    index = KnnIndex(xyz)
+    pts = tuple(to_device_f64(a) for a in xyz)
+    idx, dist, _ = index.query(pts, k=neighbours)
+    inside = torch.empty((n,), dtype=torch.uint8, device=idx.device)
+    call("at_outline_classify", _ptr(pts[0]), _ptr(pts[1]), _ptr(pts[2]), n, _ptr(idx), _ptr(dist), int(neighbours), int(CUTOUT_DOT_MODE), _ptr(inside), stream_ptr())
+    return np.nonzero(inside.cpu().numpy() == 0)[0].tolist()
+
+
 def nearest_grid_points(
     source_latitudes: NDArray[Any],
     source_longitudes: NDArray[Any],

@@ -5,6 +5,7 @@ from anemoi_transform_b200.spatial import (  # noqa: F401
     global_on_lam_mask,
     latlon_to_xyz,
     nearest_grid_points,
+    outline,
     thinning_mask,
     xyz_to_latlon,
 )

@@ -75,7 +75,8 @@ __global__ void __launch_bounds__(128)
                            const double* __restrict__ lz, long long n_lam, const double* __restrict__ gx,
                            const double* __restrict__ gy, const double* __restrict__ gz, long long nq,
                            const long long* __restrict__ nbr_idx, const double* __restrict__ nbr_dist, int k,
-                           double min_distance, double max_distance, uint8_t* __restrict__ out) {
+                           double min_distance, double max_distance, int first_triangle,
+                           uint8_t* __restrict__ out) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     const V3 g = {gx[i], gy[i], gz[i]};
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(128)
     for (int j = 1; j < k; ++j) dmin = fmin(dmin, dist[j]);  // np.min (no NaN on this path)
 
     bool inside = false;
-    for (int j = 0; j < k && !inside; ++j) {
+    for (int j = first_triangle; j < k && !inside; ++j) {
         const long long i0 = idx[j], i1 = idx[(j + 1) % k], i2 = idx[(j + 2) % k];
         if (i0 >= n_lam || i1 >= n_lam || i2 >= n_lam) continue;  // host raised IndexError already
         const V3 v0 = {lx[i0], ly[i0], lz[i0]};
@@ -229,10 +230,33 @@ extern "C" int at_cutout_classify(const double* lx, const double* ly, const doub
     const long long* idx = reinterpret_cast<const long long*>(nbr_idx);
     if (dot_mode == 1)
         cutout_classify_kernel<true><<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(
-            lx, ly, lz, n_lam, gx, gy, gz, nq, idx, nbr_dist, k, min_distance, max_distance, out);
+            lx, ly, lz, n_lam, gx, gy, gz, nq, idx, nbr_dist, k, min_distance, max_distance, 0, out);
     else
         cutout_classify_kernel<false><<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(
-            lx, ly, lz, n_lam, gx, gy, gz, nq, idx, nbr_dist, k, min_distance, max_distance, out);
+            lx, ly, lz, n_lam, gx, gy, gz, nq, idx, nbr_dist, k, min_distance, max_distance, 0, out);
+    AT_LAUNCH_CHECK("cutout_classify_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_outline_classify(const double* x, const double* y, const double* z, int64_t n,
+                                   const int64_t* nbr_idx, const double* nbr_dist, int k, int dot_mode, uint8_t* out,
+                                   void* stream) {
+    AT_REQUIRE(x && y && z && nbr_idx && nbr_dist && out, "at_outline_classify: null argument");
+    AT_REQUIRE(k >= 1 && k <= 32, "at_outline_classify: neighbours must be in [1, 32]");
+    AT_REQUIRE(n >= 0, "at_outline_classify: bad size");
+    AT_REQUIRE(dot_mode == 0 || dot_mode == 1, "at_outline_classify: dot_mode must be 0 or 1");
+    if (n == 0) return AT_OK;
+    const int64_t blocks = (n + 127) / 128;
+    AT_REQUIRE(blocks < (1ll << 31), "at_outline_classify: too large");
+    const long long* idx = reinterpret_cast<const long long*>(nbr_idx);
+    // the same triangle fan as cutout_mask over the point's own neighbours, starting at the second
+    // neighbour (the first is the point itself) and with both distance tests switched off
+    if (dot_mode == 1)
+        cutout_classify_kernel<true><<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(
+            x, y, z, n, x, y, z, n, idx, nbr_dist, k, -1.0, -1.0, 1, out);
+    else
+        cutout_classify_kernel<false><<<static_cast<unsigned>(blocks), 128, 0, as_stream(stream)>>>(
+            x, y, z, n, x, y, z, n, idx, nbr_dist, k, -1.0, -1.0, 1, out);
     AT_LAUNCH_CHECK("cutout_classify_kernel");
     return AT_OK;
 }

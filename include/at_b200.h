@@ -299,6 +299,15 @@ AT_API int at_cutout_classify(const double* lx, const double* ly, const double* 
                        const int64_t* nbr_idx, const double* nbr_dist, int k,
                        double min_distance, double max_distance, int dot_mode,
                        uint8_t* out, void* stream);
+/*
+ * outline  spatial.py:539-584 — out[i] = 1 when a ray from the Earth's centre through point i
+ * hits one of the triangles (idx[j], idx[(j+1)%k], idx[(j+2)%k]), j = 1 … k-1, of the point's
+ * own k nearest neighbours (nbr_idx / nbr_dist from a self-query; neighbour 0 is the point
+ * itself).  The outline is the set of points with out[i] == 0.
+ */
+AT_API int at_outline_classify(const double* x, const double* y, const double* z, int64_t n,
+                        const int64_t* nbr_idx, const double* nbr_dist, int k, int dot_mode,
+                        uint8_t* inside, void* stream);
 
 #ifdef __cplusplus
 }

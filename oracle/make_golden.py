@@ -60,6 +60,12 @@ def spatial_cases(sp, syn):
     out["o_x"], out["o_y"], out["o_z"] = x, y, z
     la, lo = sp.xyz_to_latlon(x, y, z)
     out["o_lat_back"], out["o_lon_back"] = la, lo
+    # outline of a scattered patch (no exactly tied neighbour distances) and of the rotated LAM
+    rng = np.random.default_rng(77)
+    out["patch_lat"], out["patch_lon"] = rng.uniform(35, 60, 900), rng.uniform(-10, 30, 900)
+    out["outline_patch"] = np.array(sp.outline(out["patch_lat"], out["patch_lon"]), dtype=np.int64)
+    out["outline_patch_n7"] = np.array(sp.outline(out["patch_lat"], out["patch_lon"], neighbours=7), dtype=np.int64)
+    out["outline_lam"] = np.array(sp.outline(lam_lat, lam_lon), dtype=np.int64)
     np.savez_compressed(GOLDEN / "spatial_small.npz", **out)
     print("spatial_small.npz:", {k: (v.shape, str(v.dtype)) for k, v in out.items() if k.startswith(("cutout", "thin", "gol", "ngp"))})
 

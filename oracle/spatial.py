@@ -177,6 +177,25 @@ def cutout_mask(lats, lons, global_lats, global_lons, cropping_distance=2.0, nei
     return _cutout_finish(mask, np.array(inside_lam, dtype=bool), max_distance_km)
 
 
+def outline(lats, lons, neighbours=5, indices=None):
+    """spatial.py:539-584 with the per-point Python loop kept literal (small inputs only).
+    `indices` may be supplied to build the fans from a given neighbour order (ties)."""
+    grid_points = _points(lats, lons)
+    if indices is None:
+        _, indices = cKDTree(grid_points).query(grid_points, k=neighbours)
+    zero = np.array([0.0, 0.0, 0.0])
+    outside = []
+    for i, (point, index) in enumerate(zip(grid_points, indices)):
+        inside = False
+        for j in range(1, neighbours):
+            inside = triangle_intersect(grid_points[index[j]], grid_points[index[(j + 1) % neighbours]], grid_points[index[(j + 2) % neighbours]], zero, point)
+            if inside:
+                break
+        if not inside:
+            outside.append(i)
+    return outside
+
+
 def _vcross(a, b):
     return np.stack([a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1], a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2], a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]], axis=1)
 

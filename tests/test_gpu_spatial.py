@@ -188,3 +188,24 @@ def test_locally_built_knn_matrix_feeds_the_regrid_filter(sp, tmp_path):
     on_source = np.nonzero((np.isin(t_lat, s_lat)) & (np.isin(t_lon, s_lon)))[0]
     for r in on_source[:5]:  # a target on a source point takes that source alone
         assert np.sort(w[r])[-1] == 1.0
+
+
+def test_outline_matches_the_reference(sp, golden_spatial):
+    """spatial.outline (self-kNN + triangle fan from the second neighbour) against the reference's
+    outputs on a scattered patch (no tied neighbour distances: exact) and on the rotated LAM."""
+    g = golden_spatial
+    assert sp.outline(g["patch_lat"], g["patch_lon"]) == g["outline_patch"].tolist()
+    assert sp.outline(g["patch_lat"], g["patch_lon"], neighbours=7) == g["outline_patch_n7"].tolist()
+    got = sp.outline(g["lam_lat"], g["lam_lon"])
+    if got != g["outline_lam"].tolist():
+        # a regular LAM has exactly tied neighbour distances: the fan order is cKDTree's traversal
+        # order there; with cKDTree's own neighbour order the classification must agree exactly
+        from scipy.spatial import cKDTree
+
+        pts = np.array(osp.latlon_to_xyz(g["lam_lat"], g["lam_lon"])).T
+        _, idx = cKDTree(pts).query(pts, k=5)
+        assert osp.outline(g["lam_lat"], g["lam_lon"], indices=idx) == g["outline_lam"].tolist()
+        d = np.sqrt(((pts[:, None, :] - pts[idx]) ** 2).sum(axis=2))
+        tied = (np.diff(d, axis=1) == 0).any(axis=1)
+        assert set(got) ^ set(g["outline_lam"].tolist()) <= set(np.nonzero(tied)[0].tolist())
+    assert sp.outline(np.zeros(0), np.zeros(0)) == []

@@ -116,3 +116,11 @@ def test_ckdtree_pads_when_k_exceeds_sources():
     src = np.array([[1.0, 0, 0], [0, 1.0, 0]])
     d, i = cKDTree(src).query(np.array([[1.0, 0, 0]]), k=3)
     assert i[0, 2] == 2 and np.isinf(d[0, 2])
+
+
+def test_outline_restatement_matches_the_reference_golden(golden_spatial):
+    """oracle.spatial.outline (spatial.py:539-584) against the imported reference's outputs."""
+    g = golden_spatial
+    assert osp.outline(g["patch_lat"], g["patch_lon"]) == g["outline_patch"].tolist()
+    assert osp.outline(g["patch_lat"], g["patch_lon"], neighbours=7) == g["outline_patch_n7"].tolist()
+    assert osp.outline(g["lam_lat"], g["lam_lon"]) == g["outline_lam"].tolist()
