@@ -370,14 +370,71 @@ __device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, 
     return best;
 }
 
+// For k > 1 the k selection passes would evaluate every candidate k times.  When the ring holds
+// at most kCandCap candidates their keys (d2, index) are computed once into the warp's slice of
+// shared memory and the passes select from there (no loads, no ring_slot shuffles, no float64
+// arithmetic per pass).
+constexpr int kCandCap = 512;
+struct CandCache {
+    double* d2;  // [kCandCap] of this warp
+    int* idx;
+};
+
+__device__ __forceinline__ void fill_cache(const KnnDev& d, const KnnLevel& L, bool level0, const Ring& r, double qx,
+                                           double qy, double qz, double ub2, int lane, const CandCache& c) {
+    for (int t0 = 0; t0 < r.total; t0 += 32) {
+        const int t = t0 + lane;
+        const int s = ring_slot(r, t < r.total ? t : r.total - 1);
+        if (t < r.total) {
+            double c2 = INFINITY;
+            long long idx = d.n;
+            if (s >= 0) {
+                double px, py, pz;
+                load_cand(d, L, level0, s, px, py, pz, idx);
+                c2 = dist2(qx, qy, qz, px, py, pz);
+                if (!(c2 < ub2)) c2 = INFINITY;
+            }
+            c.d2[t] = c2;
+            c.idx[t] = static_cast<int>(idx);
+        }
+    }
+    __syncwarp();
+}
+
+// Smallest cached key strictly greater than (prev_d2, prev_idx); d2 = +inf when none.
+__device__ __forceinline__ Cand select_cached(const KnnDev& d, const CandCache& c, int total, double prev_d2,
+                                              long long prev_idx, int lane) {
+    Cand best;
+    best.d2 = INFINITY;
+    best.idx = d.n;
+    for (int t = lane; t < total; t += 32) {
+        const double c2 = c.d2[t];
+        const long long idx = c.idx[t];
+        if (c2 < INFINITY && key_less(prev_d2, prev_idx, c2, idx) && key_less(c2, idx, best.d2, best.idx)) {
+            best.d2 = c2;
+            best.idx = idx;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best.d2, o);
+        const long long oi = __shfl_xor_sync(0xffffffffu, best.idx, o);
+        if (key_less(od, oi, best.d2, best.idx)) {
+            best.d2 = od;
+            best.idx = oi;
+        }
+    }
+    return best;
+}
+
 // Full k-NN of one query by one warp.  Lane j < k ends up holding the j-th neighbour.
 // Returns tie bits (valid when want_tie).
 //
 // Only the first `max_levels` levels are tried; `done` tells whether the answer is final
 // (the caller hands unfinished queries to the tree search).
+template <bool CACHE>
 __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double qy, double qz, int k,
                                             double ub2, bool want_tie, int lane, int max_levels, bool& done,
-                                            double& my_d2, long long& my_idx) {
+                                            double& my_d2, long long& my_idx, const CandCache& cache) {
     unsigned tie = 0;
     done = true;
     for (int level = 0; level < max_levels; ++level) {
@@ -393,8 +450,11 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         double pd2 = -1.0;
         long long pidx = -1;
         int found = 0;
+        const bool cached = CACHE && k > 1 && r.total <= kCandCap;  // warp-uniform
+        if (cached) fill_cache(d, L, level == 0, r, qx, qy, qz, ub2, lane, cache);
         for (int j = 0; j < k; ++j) {
-            const Cand c = select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+            const Cand c = cached ? select_cached(d, cache, r.total, pd2, pidx, lane)
+                                  : select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
             if (!(c.d2 < INFINITY)) break;
             if (j > 0 && c.d2 == pd2) tie |= 1u;
             if (lane == j) {
@@ -408,11 +468,14 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         const bool complete = found == k && pd2 < L.cover2;
         if (complete || last || ub2 <= L.cover2) {
             if (want_tie && found == k) {
-                const Cand c = select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+                const Cand c = cached ? select_cached(d, cache, r.total, pd2, pidx, lane)
+                                      : select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
                 if (c.d2 == pd2) tie |= 2u;
             }
+            __syncwarp();  // the cache is rewritten by the next level / query
             return tie;
         }
+        __syncwarp();
     }
     done = false;
     return tie;
@@ -420,19 +483,27 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
 
 constexpr long long kPending = -1;  // idx_out[q*k] of a query the near search left to the tree search
 
+template <bool CACHE>  // CACHE: k > 1, candidate keys cached in shared memory (knn_one)
 __global__ void __launch_bounds__(256)
     knn_query_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
                      const double* __restrict__ qz, long long nq, int k, double ub2, int near_levels,
                      long long* __restrict__ idx_out, double* __restrict__ dist_out,
                      uint8_t* __restrict__ tie_out) {
-    const int lane = threadIdx.x & 31;
+    // per-warp candidate cache (k > 1 only; the k = 1 launch passes no shared memory)
+    extern __shared__ __align__(16) unsigned char s_cache[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    CandCache cache = {nullptr, nullptr};
+    if (CACHE) {
+        cache.d2 = reinterpret_cast<double*>(s_cache) + warp * kCandCap;
+        cache.idx = reinterpret_cast<int*>(s_cache + (blockDim.x >> 5) * kCandCap * sizeof(double)) + warp * kCandCap;
+    }
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
         const double x = qx[q], y = qy[q], z = qz[q];
         double d2;
         long long idx;
         bool done;
-        const unsigned tie = knn_one(d, x, y, z, k, ub2, tie_out != nullptr, lane, near_levels, done, d2, idx);
+        const unsigned tie = knn_one<CACHE>(d, x, y, z, k, ub2, tie_out != nullptr, lane, near_levels, done, d2, idx, cache);
         if (!done) {
             if (lane == 0) idx_out[q * k] = kPending;
             continue;
@@ -573,7 +644,8 @@ __global__ void __launch_bounds__(256)
         double d2;
         long long idx;
         bool done;
-        knn_one(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d.n_levels, done, d2, idx);
+        const CandCache no_cache = {nullptr, nullptr};
+        knn_one<false>(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d.n_levels, done, d2, idx, no_cache);
         const double second = __shfl_sync(0xffffffffu, d2, 1);
         best = fmin(best, second);
     }
@@ -841,8 +913,14 @@ extern "C" int at_knn_query(const at_knn_t* k, const double* qx, const double* q
     // decide (queries far from every source) goes to the per-thread tree search
     const int n_grid = k->dev.n_levels - 1;
     const int near_levels = std::min(2, n_grid);
-    knn_query_kernel<<<query_blocks(nq), 256, 0, as_stream(stream)>>>(
-        k->dev, qx, qy, qz, nq, kk, ub2, near_levels, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+    // k > 1: 8 warps x kCandCap cached keys (float64 d2 + int32 index) = 48 KB per CTA
+    const size_t cache_bytes = kk > 1 ? static_cast<size_t>(8) * kCandCap * (sizeof(double) + sizeof(int)) : 0;
+    if (kk > 1)
+        knn_query_kernel<true><<<query_blocks(nq), 256, cache_bytes, as_stream(stream)>>>(
+            k->dev, qx, qy, qz, nq, kk, ub2, near_levels, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+    else
+        knn_query_kernel<false><<<query_blocks(nq), 256, 0, as_stream(stream)>>>(
+            k->dev, qx, qy, qz, nq, kk, ub2, near_levels, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
     AT_LAUNCH_CHECK("knn_query_kernel");
     const long long tree_blocks = (nq + 127) / 128;
     AT_REQUIRE(tree_blocks < (1ll << 31), "at_knn_query: too many queries");
