@@ -23,7 +23,7 @@ pytestmark = [pytest.mark.reference, pytest.mark.skipif(not REF_TESTS.exists(), 
 
 # host-logic test modules of the reference that exercise code on the hot path's host side
 # (test_fields.py imports `src.anemoi.transform.fields` by path, i.e. the reference's own file, so it cannot be redirected)
-MODULES = ["test_matching.py", "test_grouping.py", "test_filter.py", "test_dispatchingfilter.py"]
+MODULES = ["test_matching.py", "test_grouping.py", "test_filter.py", "test_dispatchingfilter.py", "test_create.py"]
 
 
 def test_reference_host_tests_pass_against_this_package(tmp_path):
@@ -40,4 +40,4 @@ def test_reference_host_tests_pass_against_this_package(tmp_path):
         [sys.executable, "-c", "import anemoi.transform.filter as f; print(f.SingleFieldFilter.__module__)"], capture_output=True, text=True, env=env
     ).stdout, "the shim did not resolve to this package"
     assert r.returncode == 0 and m, tail
-    assert int(m.group(1)) >= 40, tail
+    assert int(m.group(1)) >= 41, tail
