@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import threading
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
 from pathlib import Path
 
 LIB_NAME = "libat_b200.so"
@@ -29,6 +29,7 @@ EPI_OUT_PER_GROUP = {
     EPI_AFFINE: 4, EPI_AFFINE_INV: 4, EPI_EXP: 4, EPI_LOG: 4, EPI_IMPUTE_NAN: 4, EPI_COSSIN: 8, EPI_ATAN2: 2,
     EPI_RT2D: 2, EPI_RT2RTD: 6, EPI_DT2R: 2, EPI_DT2DTR: 6,
 }  # fmt: skip
+HOSTIO_SPMM, HOSTIO_GATHER = 0, 1
 CMP_NOT_NAN = 6
 COL_CLIP_LO, COL_CLIP_HI, COL_MASK = 1, 2, 4
 
@@ -67,7 +68,7 @@ PROTOTYPES = {
     "at_spmm": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p, c_int, c_int64, c_int64, c_int, c_void_p]),
     "at_epilogue_create": (c_int, [POINTER(EpiSegment), c_int32, POINTER(EpiCol), c_int32, POINTER(c_void_p)]),
     "at_epilogue_destroy": (c_int, [c_void_p]),
-    "at_spmm_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
+    "at_spmm_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "at_pointwise": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "at_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "at_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
@@ -78,9 +79,32 @@ PROTOTYPES = {
     "at_pipeline_create": (c_int, [c_void_p, c_int32, POINTER(c_void_p)]),
     "at_pipeline_destroy": (c_int, [c_void_p]),
     "at_pipeline_regrid": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64]),
+    "at_pinned_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
+    "at_pinned_alloc_many": (c_int, [c_size_t, c_int64, POINTER(c_void_p)]),
+    "at_pinned_free": (c_int, [c_void_p]),
+    "at_pinned_trim": (c_int, []),
+    "at_pinned_stats": (c_int, [POINTER(c_size_t), POINTER(c_size_t)]),
+    "at_hostio_create": (c_int, [c_int32, POINTER(c_void_p)]),
+    "at_hostio_destroy": (c_int, [c_void_p]),
+    "at_hostio_threads": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32)]),
+    "at_hostio_upload": (c_int, [c_void_p, POINTER(c_void_p), c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "at_hostio_download": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, POINTER(c_void_p), c_void_p, POINTER(c_int64)]),
+    "at_hostio_wait": (c_int, [c_void_p, c_int64]),
+    "at_hostio_regrid": (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int64, c_int64, c_int, c_void_p, c_int64, POINTER(c_void_p), c_void_p, POINTER(c_int64)],
+    ),
     "at_knn_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_void_p)]),
     "at_knn_destroy": (c_int, [c_void_p]),
     "at_knn_query": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "at_knn_query_gather": (
+        c_int,
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p],
+    ),
+    "at_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "at_peer_free": (c_int, [c_void_p]),
+    "at_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "at_peer_close": (c_int, [c_void_p]),
     "at_ball_mark": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p]),
     "at_min_nn_distance": (c_int, [c_void_p, c_int64, c_int64, POINTER(c_double), c_void_p]),
     "at_compact_mask": (c_int, [c_void_p, c_int64, c_void_p, POINTER(c_int64), c_void_p]),

@@ -207,9 +207,15 @@ class Epilogue:
     def apply_fused(self, csr: CsrMatrix, X, out=None, row_mask=None):
         """Y = epilogue(A · X)."""
         torch = _torch()
+        if X.dim() != 2 or X.shape[0] != csr.shape[1]:
+            raise ValueError(f"dimension mismatch: matrix has {csr.shape[1]} columns, X has shape {tuple(X.shape)}")
+        if X.shape[1] < self.n_in_cols:
+            raise ValueError(f"the epilogue reads {self.n_in_cols} input columns, X has {X.shape[1]}")
+        if X.dtype != torch.float32 or X.stride(1) != 1:
+            raise ValueError("apply_fused: X must be a row-major float32 batch")
         if out is None:
             out = empty_batch(csr.shape[0], self.n_out_cols, torch.float32, X.device)
-        call("at_spmm_fused", csr.handle, self.handle, _ptr(X), X.stride(0), _ptr(out), out.stride(0), _ptr(row_mask), stream_ptr())
+        call("at_spmm_fused", csr.handle, self.handle, _ptr(X), X.shape[0], X.stride(0), _ptr(out), out.stride(0), _ptr(row_mask), stream_ptr())
         return out
 
 
@@ -375,106 +381,168 @@ def compare_mask(values, op: int, threshold: float):
     return mask
 
 
-_STAGING_BYTES = 128 << 20  # per slot; two slots pinned + two on the device, allocated once
-_COPY_THREADS = None
-_N_COPY_THREADS = 1
-_RING = None
+# ---------------------------------------------------------------- host <-> device -------
+class PinnedBlock:
+    """A block of the library's page-locked host pool, exposed to numpy through the array
+    interface; the block returns to the pool when the last array viewing it is collected."""
+
+    __slots__ = ("ptr", "nbytes", "__array_interface__", "__weakref__")
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _cabi.load().at_pinned_free(c_void_p(self.ptr))
+        except Exception:  # interpreter shutdown
+            pass
 
 
-def _chunk_fields(n_fields: int, field_bytes: int, chunk: int | None) -> int:
-    if chunk is None:
-        chunk = max(1, min(256, _STAGING_BYTES // max(1, field_bytes)))
-    return max(1, min(int(chunk), n_fields))
+def _array_on_block(ptr: int, n: int, dtype) -> np.ndarray:
+    dtype = np.dtype(dtype)
+    return np.asarray(PinnedBlock(ptr, n * dtype.itemsize)).view(dtype)
 
 
-def _parallel_copy(pairs) -> None:
-    """dst[...] = src for (dst, src) numpy pairs; big batches are spread over host threads
-    (numpy releases the GIL while it copies).  One task per thread, not per field: a pool task
-    costs tens of microseconds, a 260 KB field copies in about as long."""
-    global _COPY_THREADS, _N_COPY_THREADS
-    total = sum(d.nbytes for d, _ in pairs)
-    if total < (4 << 20):
-        for d, s in pairs:
-            np.copyto(d, s, casting="unsafe")
-        return
-    if _COPY_THREADS is None:
-        import os
-        from concurrent.futures import ThreadPoolExecutor
-
-        _N_COPY_THREADS = int(os.environ.get("AT_B200_COPY_THREADS", 0)) or max(1, min(8, (len(os.sched_getaffinity(0)) or 2) - 1))
-        _COPY_THREADS = ThreadPoolExecutor(max_workers=_N_COPY_THREADS, thread_name_prefix="at-copy")
-    if len(pairs) < _N_COPY_THREADS:  # few large fields: split them
-        parts = -(-_N_COPY_THREADS // len(pairs))
-        split = []
-        for d, s in pairs:
-            cuts = np.linspace(0, d.size, parts + 1).astype(np.int64)
-            split += [(d[a:b], s[a:b]) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
-        pairs = split
-    n_groups = min(_N_COPY_THREADS, len(pairs))
-    groups = [pairs[g::n_groups] for g in range(n_groups)]
-
-    def work(group):
-        for d, s in group:
-            np.copyto(d, s, casting="unsafe")
-
-    futures = [_COPY_THREADS.submit(work, g) for g in groups[1:]]
-    work(groups[0])  # the calling thread takes a share
-    for f in futures:
-        f.result()
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """np.empty in page-locked host memory (a block of the library's pool): uploads of such
+    arrays and downloads into them are DMA-ed in place, without a staging copy.  Decoders that
+    feed the filters of this package can allocate their field arrays here."""
+    require_cuda()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = c_void_p()
+    call("at_pinned_alloc", max(1, n * dtype.itemsize), byref(p))
+    return _array_on_block(p.value, n, dtype).reshape(shape)
 
 
-class _StagingRing:
-    """Two pinned host slots and two device slots of raw bytes, reused by every upload /
-    download of the process (pinning memory is slow; do it once)."""
-
-    def __init__(self, nbytes: int):
-        torch = _torch()
-        self.nbytes = nbytes
-        self.pinned = [torch.empty((nbytes,), dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.device = [torch.empty((nbytes,), dtype=torch.uint8, device="cuda") for _ in range(2)]
-        self.events = [None, None]
-        self.busy = False
-
-    def wait(self, slot: int) -> None:
-        if self.events[slot] is not None:
-            self.events[slot].synchronize()
-            self.events[slot] = None
-
-    def record(self, slot: int) -> None:
-        torch = _torch()
-        ev = torch.cuda.Event()
-        ev.record()
-        self.events[slot] = ev
-
-    def release(self) -> None:
-        self.wait(0)
-        self.wait(1)
-        self.busy = False
+def pinned_fields(n_fields: int, n_points: int, dtype) -> tuple[list[np.ndarray] | None, object]:
+    """n_fields pool arrays of n_points elements and the ctypes pointer array naming them, or
+    (None, None) when the pool is exhausted (callers then use ordinary numpy memory)."""
+    dtype = np.dtype(dtype)
+    ptrs = (c_void_p * n_fields)()
+    try:
+        call("at_pinned_alloc_many", max(1, n_points * dtype.itemsize), n_fields, ptrs)
+    except _cabi.NativeCallError as e:
+        if e.code != _cabi.AT_ERR_NOMEM:
+            raise
+        return None, None
+    return [_array_on_block(ptrs[j], n_points, dtype) for j in range(n_fields)], ptrs
 
 
-def _staging_ring(nbytes: int) -> _StagingRing:
-    """The process-wide ring, grown when a chunk needs more (per device, single-threaded use)."""
-    global _RING
-    torch = _torch()
-    nbytes = round_up(max(nbytes, 1 << 20), 1 << 20)
-    dev = torch.cuda.current_device()
-    if _RING is None or _RING.nbytes < nbytes or _RING.device[0].device.index != dev or _RING.busy:
-        ring = _StagingRing(nbytes)
-        if _RING is None or not _RING.busy:
-            _RING = ring
-    else:
-        ring = _RING
-    ring.busy = True
-    return ring
+def pinned_pool_stats() -> tuple[int, int]:
+    """(bytes in use, bytes reserved) of the page-locked pool."""
+    from ctypes import c_size_t
+
+    a, b = c_size_t(), c_size_t()
+    call("at_pinned_stats", byref(a), byref(b))
+    return a.value, b.value
+
+
+def pinned_pool_trim() -> None:
+    call("at_pinned_trim")
+
+
+def _host_ptr(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]
+
+
+def _pointer_array(arrays: Sequence[np.ndarray]):
+    return (c_void_p * len(arrays))(*[a.__array_interface__["data"][0] for a in arrays])
+
+
+class HostIO:
+    """Owner of the process's `at_hostio_t` engine for the current device."""
+
+    _engines: dict[int, "HostIO"] = {}
+
+    def __init__(self, n_threads: int = 0):
+        torch = require_cuda()
+        self.device = torch.cuda.current_device()
+        h = c_void_p()
+        call("at_hostio_create", int(n_threads), byref(h))
+        self._h = h
+        from ctypes import c_int32
+
+        t, nt = c_int32(), c_int32()
+        call("at_hostio_threads", self._h, byref(t), byref(nt))
+        self.n_threads, self.nontemporal = t.value, bool(nt.value)
+
+    @classmethod
+    def get(cls) -> "HostIO":
+        torch = require_cuda()
+        dev = torch.cuda.current_device()
+        io = cls._engines.get(dev)
+        if io is None:
+            import os
+
+            n = int(os.environ.get("AT_B200_COPY_THREADS", 0))
+            local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
+            if n <= 0 and local > 1:
+                # several ranks on one box share its cores (two hardware threads per core assumed)
+                n = max(1, min(8, len(os.sched_getaffinity(0)) // 2 // local))
+            io = cls._engines[dev] = cls(n)  # 0: one staging thread per physical core
+        return io
+
+    @property
+    def handle(self) -> c_void_p:
+        return self._h
+
+    def upload(self, arrays: Sequence[np.ndarray], pm, col0: int = 0) -> None:
+        """pm[:, col0 + j] = arrays[j] (contiguous 1-D host arrays of pm's dtype)."""
+        n = len(arrays)
+        if n == 0:
+            return
+        esz = pm.element_size()
+        call("at_hostio_upload", self._h, _pointer_array(arrays), n, int(arrays[0].size), esz, c_void_p(pm.data_ptr() + col0 * esz), pm.stride(0), stream_ptr())
+
+    def download(self, pm, col0: int, dests: Sequence[np.ndarray], ptrs=None) -> int:
+        """dests[j][:] = pm[:, col0 + j]; → ticket (-1 when already complete)."""
+        n = len(dests)
+        if n == 0:
+            return -1
+        esz = pm.element_size()
+        ticket = c_int64(-1)
+        call("at_hostio_download", self._h, c_void_p(pm.data_ptr() + col0 * esz), pm.stride(0), n, int(pm.shape[0]), esz, ptrs if ptrs is not None else _pointer_array(dests), stream_ptr(), byref(ticket))
+        return ticket.value
+
+    def wait(self, ticket: int) -> None:
+        if ticket >= 0:
+            call("at_hostio_wait", self._h, ticket)
+
+
+class Transfer:
+    """An asynchronous device-to-host transfer of the I/O engine (an `at_hostio` ticket)."""
+
+    __slots__ = ("ticket", "done")
+
+    def __init__(self, ticket: int):
+        self.ticket, self.done = ticket, ticket < 0
+
+    def wait(self) -> None:
+        if not self.done:
+            self.done = True
+            HostIO.get().wait(self.ticket)
 
 
 class DeviceBatch:
-    """A batch of fields resident in HBM, point-major: data[n_points, ld], ld % 4 == 0."""
+    """A batch of fields resident in HBM, point-major: data[n_points, ld], ld % 4 == 0.
+
+    Host copies of the columns (`_host`) appear when they are first needed — or ahead of need,
+    when a filter knows its results are headed for the host (`prefetch`, the streamed regrid)
+    — as arrays of the page-locked pool that the DMA engine fills directly; `_ticket[j]` is the
+    transfer column j's array is waiting for."""
+
+    #: host bytes fetched per lazy download (a reader walking the columns misses once per window)
+    window_bytes = 256 << 20
 
     def __init__(self, data, n_fields: int):
         self.data = data
         self.n_fields = int(n_fields)
-        self._host = None  # per-column host arrays downloaded at the first to_numpy(), handed out once
+        self._host: list | None = None
+        self._ticket: list[Transfer | None] | None = None
+        self._n_points = int(data.shape[0]) if data is not None else 0
+        self._dtype = None
 
     @property
     def n_points(self) -> int:
@@ -486,12 +554,11 @@ class DeviceBatch:
 
     @classmethod
     def from_host_fields(cls, arrays: Sequence[np.ndarray], chunk: int | None = None) -> "DeviceBatch":
-        """Upload F host fields (each [n_points]) and pack them point-major.
-
-        Fields go up in chunks: host threads copy a chunk's arrays from wherever they live
-        (pageable memory as a rule) into a pinned staging slot, one async H2D moves the slot
-        into a field-major device buffer, `at_transpose` writes it into its columns of the
-        batch.  Two slots, so the host copies of chunk k+1 overlap the DMA of chunk k."""
+        """Upload F host fields (each [n_points]) and pack them point-major (`at_hostio_upload`:
+        worker threads stage pageable arrays into pinned slots, one H2D per piece, one
+        `at_transpose` per chunk; page-locked arrays are read in place).  All fields take the
+        batch's dtype — the widest of theirs; callers that must keep per-field dtypes batch
+        runs of equal dtype (`batching.group_by_dtype`)."""
         torch = require_cuda()
         n_fields = len(arrays)
         if n_fields == 0:
@@ -505,67 +572,95 @@ class DeviceBatch:
         for i, v in enumerate(views):
             if v.size != n_points:
                 raise ValueError(f"field {i} has {v.size} points, expected {n_points}")
-        ld = round_up(n_fields, 4)
+        views = [v if (v.dtype == dtype and v.flags.c_contiguous) else np.ascontiguousarray(v, dtype=dtype) for v in views]
         pm = empty_batch(n_points, n_fields, tdtype, "cuda")
-        chunk = _chunk_fields(n_fields, n_points * dtype.itemsize, chunk)
-        ring = _staging_ring(chunk * n_points * dtype.itemsize)
-        pins = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.pinned]
-        devs = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.device]
-        try:
-            for k, c0 in enumerate(range(0, n_fields, chunk)):
-                slot = k % 2
-                nf = min(chunk, n_fields - c0)
-                ring.wait(slot)  # the DMA that last read this pinned slot
-                _parallel_copy([(pins[slot][j].numpy(), views[c0 + j]) for j in range(nf)])
-                devs[slot][:nf].copy_(pins[slot][:nf], non_blocking=True)
-                ring.record(slot)
-                call("at_transpose", _ptr(devs[slot]), nf, n_points, n_points, c_void_p(pm.data_ptr() + c0 * pm.element_size()), ld, pm.element_size(), stream_ptr())
-        finally:
-            ring.release()
+        HostIO.get().upload(views, pm)
         return cls(pm, n_fields)
-
-    def _download(self, dests: Sequence[np.ndarray], first_col: int = 0, chunk: int | None = None) -> None:
-        """dests[j][:] = column first_col + j: chunks are transposed field-major on the device,
-        moved into a pinned slot by one async D2H, and copied into the destinations by host
-        threads while the next chunk is in flight."""
-        torch = _torch()
-        tdtype = self.data.dtype
-        n_points, esz, n = self.n_points, self.data.element_size(), len(dests)
-        chunk = _chunk_fields(n, n_points * esz, chunk)
-        ring = _staging_ring(chunk * n_points * esz)
-        pins = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.pinned]
-        devs = [r.view(tdtype)[: chunk * n_points].view(chunk, n_points) for r in ring.device]
-        pending = None
-
-        def drain(p):
-            slot, c0, nf = p
-            ring.wait(slot)
-            _parallel_copy([(dests[c0 + j], pins[slot][j].numpy()) for j in range(nf)])
-
-        try:
-            for k, c0 in enumerate(range(0, n, chunk)):
-                slot = k % 2
-                nf = min(chunk, n - c0)
-                call("at_transpose", c_void_p(self.data.data_ptr() + (first_col + c0) * esz), n_points, nf, self.data.stride(0), _ptr(devs[slot]), n_points, esz, stream_ptr())
-                pins[slot][:nf].copy_(devs[slot][:nf], non_blocking=True)
-                ring.record(slot)
-                if pending is not None:
-                    drain(pending)
-                pending = (slot, c0, nf)
-            if pending is not None:
-                drain(pending)
-        finally:
-            ring.release()
 
     def _np_dtype(self):
         if self.data is None:
-            return self._host[0].dtype
+            return self._dtype
         return np.dtype(np.float32 if self.data.dtype == _torch().float32 else np.float64)
+
+    # -- host copies ----------------------------------------------------------------------
+    def _ensure_host_lists(self) -> None:
+        if self._host is None:
+            self._host = [None] * self.n_fields
+            self._ticket = [None] * self.n_fields
+
+    def _start_download(self, first: int, count: int) -> None:
+        """Begin moving columns [first, first + count) that have no host copy yet into pool
+        arrays (asynchronous); pageable arrays when the pool is exhausted (synchronous)."""
+        self._ensure_host_lists()
+        cols = [j for j in range(first, first + count) if self._host[j] is None]
+        io = HostIO.get()
+        # runs of consecutive columns go in one call
+        run: list[int] = []
+        for j in cols + [-1]:
+            if run and j == run[-1] + 1:
+                run.append(j)
+                continue
+            if run:
+                arrays, ptrs = pinned_fields(len(run), self.n_points, self._np_dtype())
+                if arrays is None:
+                    arrays, ptrs = [np.empty((self.n_points,), dtype=self._np_dtype()) for _ in run], None
+                transfer = Transfer(io.download(self.data, run[0], arrays, ptrs))
+                for k, c in enumerate(run):
+                    self._host[c], self._ticket[c] = arrays[k], transfer
+            run = [j] if j >= 0 else []
+
+    def adopt_host_arrays(self, arrays: Sequence[np.ndarray], transfer: "Transfer") -> None:
+        """Host copies produced together with the batch (the streamed regrid's outputs)."""
+        self._host = list(arrays)
+        self._ticket = [transfer] * len(arrays)
+        if self.data is None and arrays:
+            self._n_points, self._dtype = int(arrays[0].size), arrays[0].dtype
+
+    def prefetch(self) -> None:
+        """Start the download of every column now: the caller expects `to_numpy()` soon."""
+        if self.data is not None:
+            self._start_download(0, self.n_fields)
+
+    def prefetch_columns(self, cols: Sequence[int]) -> None:
+        """`prefetch` of the listed (sorted) columns only — a fused launch leaves padding
+        columns between its segments that belong to no field."""
+        if self.data is None or not cols:
+            return
+        start = prev = cols[0]
+        for c in list(cols[1:]) + [None]:
+            if c is not None and c == prev + 1:
+                prev = c
+                continue
+            self._start_download(start, prev - start + 1)
+            if c is not None:
+                start = prev = c
+
+    def _wait(self, col: int) -> None:
+        t = self._ticket[col]
+        if t is not None:
+            t.wait()
+
+    def _wait_all(self) -> None:
+        if self._ticket:
+            for t in {id(t): t for t in self._ticket if t is not None and not t.done}.values():
+                t.wait()
+
+    def __del__(self):
+        # a DMA still writing into pool arrays must finish before they are recycled
+        try:
+            self._wait_all()
+        except Exception:
+            pass
 
     def to_host_fields(self, chunk: int | None = None) -> np.ndarray:
         """→ numpy [n_fields, n_points] (field-major), a fresh array."""
         host = np.empty((self.n_fields, self.n_points), dtype=self._np_dtype())
-        self._download([host[j] for j in range(self.n_fields)], 0, chunk)
+        if self.data is None:
+            self._wait_all()
+            for j in range(self.n_fields):
+                host[j] = self._host[j]
+            return host
+        HostIO.get().download(self.data, 0, [host[j] for j in range(self.n_fields)])
         return host
 
     def offload(self) -> None:
@@ -574,39 +669,135 @@ class DeviceBatch:
         `take_column` hands out copies of the host arrays."""
         if self.data is None:
             return
-        if self._host is None:
-            self._host = [np.empty((self.n_points,), dtype=self._np_dtype()) for _ in range(self.n_fields)]
-            self._download(self._host)
-        else:  # columns already handed out were the callers'; fetch them again for our own copy
-            missing = [j for j, a in enumerate(self._host) if a is None]
-            for j in missing:
-                self._host[j] = np.empty((self.n_points,), dtype=self._np_dtype())
-                self._download([self._host[j]], first_col=j)
-        self._n_points = self.n_points
+        self._start_download(0, self.n_fields)
+        self._wait_all()
+        self._n_points, self._dtype = self.n_points, self._np_dtype()
         self.data = None
 
     def take_column(self, col: int) -> np.ndarray:
         """A fresh host array with the values of column `col`, owned by the caller.
 
-        The first request downloads every column of the batch (one pass, one array per field);
-        each array is handed out once without a further copy.  A column asked for again is
-        downloaded again (the device copy is the source of truth — callers may mutate what
-        they were given, e.g. apply_mask.py:184-185)."""
+        A column without a host copy triggers the download of a window of columns starting at
+        it (not of the whole batch); each array is handed out once without a further copy.  A
+        column asked for again is downloaded again (the device copy is the source of truth —
+        callers may mutate what they were given, e.g. apply_mask.py:184-185)."""
+        if not 0 <= col < self.n_fields:
+            raise IndexError(f"column {col} of a batch of {self.n_fields} fields")
         if self.data is None:  # offloaded: the host arrays are the only copy
+            self._wait(col)
             return self._host[col].copy()
-        if self._host is None:
-            self._host = [np.empty((self.n_points,), dtype=self._np_dtype()) for _ in range(self.n_fields)]
-            self._download(self._host)
-        arr = self._host[col]
-        if arr is None:
-            arr = np.empty((self.n_points,), dtype=self._np_dtype())
-            self._download([arr], first_col=col)
-        else:
-            self._host[col] = None
+        self._ensure_host_lists()
+        if self._host[col] is None:
+            per_field = max(1, self.n_points * self.data.element_size())
+            self._start_download(col, min(self.n_fields - col, max(1, self.window_bytes // per_field)))
+        self._wait(col)
+        arr, self._host[col] = self._host[col], None
         return arr
 
     def host_column(self, col: int) -> np.ndarray:
         return self.take_column(col)
+
+    def locate(self, col: int) -> tuple["DeviceBatch", int]:
+        """(batch, column) of output `col` — itself (see pointwise.SplitOutput)."""
+        return self, col
+
+
+_HOST_BOUND = [True]
+
+
+def results_are_host_bound() -> bool:
+    """Whether a filter should start moving its results to the host as it produces them (the
+    caller of a stand-alone `forward` reads them next) or leave them in HBM for the next
+    filter of a pipeline."""
+    return _HOST_BOUND[0]
+
+
+class results_stay_on_device:
+    """Context of the non-final filters of a `Pipeline`: no eager download of their results."""
+
+    def __enter__(self):
+        self._saved, _HOST_BOUND[0] = _HOST_BOUND[0], False
+
+    def __exit__(self, *exc):
+        _HOST_BOUND[0] = self._saved
+
+
+class StreamedRegrid:
+    """One `at_hostio_regrid` job: host fields in, a `DeviceBatch` with host copies out.
+
+    The native call runs on a helper thread (it releases the GIL for its whole duration), so
+    the caller can build the output FieldList while the fields stream through the GPU;
+    `join()` returns once every input byte has been consumed — the results keep arriving in
+    their pool arrays behind the batch's transfer."""
+
+    def __init__(self, op: int, csr: "CsrMatrix | None", index, n_tgt: int, y_dtype, arrays: Sequence[np.ndarray], keep_resident: bool, to_host: bool):
+        import threading
+
+        torch = require_cuda()
+        if not (keep_resident or to_host):
+            raise ValueError("StreamedRegrid: nothing to produce")
+        n = len(arrays)
+        n_src = int(arrays[0].size)
+        x_np = arrays[0].dtype
+        y_np = np.dtype(np.float32 if y_dtype == torch.float32 else np.float64)
+        self._io = HostIO.get()
+        self._keep = (arrays, csr, index)  # alive until the native call returns
+        data = empty_batch(n_tgt, n, y_dtype, "cuda") if keep_resident else None
+        self.batch = DeviceBatch(data, n)
+        if data is None:
+            self.batch._n_points, self.batch._dtype = n_tgt, y_np
+        self._out, out_ptrs, pooled = None, None, False
+        if to_host:
+            # raw pool blocks now, numpy views on them once the native call is running
+            out_ptrs = (c_void_p * n)()
+            try:
+                call("at_pinned_alloc_many", max(1, n_tgt * y_np.itemsize), n, out_ptrs)
+                pooled = True
+            except _cabi.NativeCallError as e:
+                if e.code != _cabi.AT_ERR_NOMEM:
+                    raise
+                # pool exhausted: pageable destinations, filled synchronously
+                self._out = [np.empty((n_tgt,), dtype=y_np) for _ in range(n)]
+                out_ptrs = _pointer_array(self._out)
+        self._ticket = c_int64(-1)
+        self._error: BaseException | None = None
+        args = (
+            "at_hostio_regrid",
+            self._io.handle,
+            int(op),
+            csr.handle if csr is not None else None,
+            _ptr(index),
+            int(n_tgt),
+            _pointer_array(arrays),
+            n,
+            n_src,
+            AT_F32 if x_np == np.float32 else AT_F64,
+            _ptr(data),
+            int(data.stride(0)) if data is not None else 0,
+            out_ptrs,
+            stream_ptr(),
+            byref(self._ticket),
+        )
+
+        def run():
+            try:
+                call(*args)
+            except BaseException as e:  # re-raised by join()
+                self._error = e
+
+        self._thread = threading.Thread(target=run, name="at-regrid-stream", daemon=True)
+        self._thread.start()
+        if pooled:
+            self._out = [_array_on_block(out_ptrs[j], n_tgt, y_np) for j in range(n)]
+
+    def join(self) -> DeviceBatch:
+        self._thread.join()
+        self._keep = None
+        if self._error is not None:
+            raise self._error
+        if self._out is not None:
+            self.batch.adopt_host_arrays(self._out, Transfer(self._ticket.value))
+        return self.batch
 
 
 class HostPipeline:

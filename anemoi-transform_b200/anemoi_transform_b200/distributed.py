@@ -103,23 +103,179 @@ def sharded_query(n_queries: int, local_query: Callable[[int, int], "object"]):
     return all_gather_rows(local_query(lo, hi), n_queries)
 
 
+# ---- fused query + all-gather over NVLink peer memory ----------------------------------------
+class _DevicePointer:
+    """A raw device allocation presented to torch through the CUDA array interface."""
+
+    def __init__(self, ptr: int, shape: tuple[int, ...], typestr: str):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+class PeerBuffers:
+    """One device buffer per rank that every rank of the box can address (cudaIpc over
+    NVLink / NVSwitch): `ptrs[r]` is rank r's buffer as seen from this process."""
+
+    def __init__(self, nbytes: int):
+        import ctypes
+
+        import torch
+
+        from ._cabi import call
+
+        dist = _dist()
+        self.rank, self.world = world()
+        self.nbytes = int(nbytes)
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        call("at_peer_alloc", self.nbytes, ctypes.byref(own), handle)
+        self._own = own.value
+        handles: list = [None] * self.world
+        dist.all_gather_object(handles, handle.raw)
+        self.ptrs: list[int] = []
+        self._opened: list[int] = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.ptrs.append(self._own)
+                continue
+            p = ctypes.c_void_p()
+            call("at_peer_open", ctypes.create_string_buffer(h, 64), ctypes.byref(p))
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+        torch.cuda.synchronize()
+        dist.barrier()  # every buffer is zeroed and mapped before anyone writes into a peer
+
+    def close(self) -> None:
+        import ctypes
+
+        import torch
+
+        from ._cabi import call
+
+        if self._own is None:
+            return
+        torch.cuda.synchronize()
+        if _dist().is_initialized():
+            _dist().barrier()  # nobody is still storing into a buffer about to be freed
+        for p in self._opened:
+            call("at_peer_close", ctypes.c_void_p(p))
+        call("at_peer_free", ctypes.c_void_p(self._own))
+        self._own, self._opened, self.ptrs = None, [], []
+
+
+class ShardedKnnQuery:
+    """k nearest sources of a query set sharded over the ranks; every rank ends up with the
+    full [n_queries, k] index array in HBM.
+
+    On NCCL-capable boxes the all-gather is fused into the search (`at_knn_query_gather`): the
+    query kernels store each index into every rank's gather buffer through NVLink peer mappings
+    and a one-warp kernel exchanges arrival flags — no collective launch, no staging copy.  When
+    peer mapping is unavailable the queries write straight into this rank's slice of a
+    preallocated buffer and NCCL all-gathers it in place (no per-step allocation either)."""
+
+    def __init__(self, index, qxyz, k: int = 1, distance_upper_bound: float = float("inf"), mode: str = "auto"):
+        import torch
+
+        from .device import to_device_f64
+
+        self.index, self.k, self.ub = index, int(k), float(distance_upper_bound)
+        self.rank, self.world = world()
+        self.nq = int(qxyz[0].shape[0])
+        self.per = -(-self.nq // self.world) if self.nq else 0
+        self.lo, self.hi = shard_range(self.nq, self.rank, self.world)
+        self.q = tuple(to_device_f64(a[self.lo : self.hi]) for a in qxyz)
+        self._all_q = qxyz
+        self.epoch = 0
+        self.peers = None
+        rows = max(1, self.world * self.per)
+        self.mode = "local" if self.world == 1 else mode
+        if self.mode in ("auto", "peer"):
+            try:
+                self._slot_bytes = -(-rows * self.k * 8 // 256) * 256
+                self.peers = PeerBuffers(2 * self._slot_bytes + 256)
+                self.mode = "peer"
+            except Exception as e:
+                if mode == "peer":
+                    raise
+                import logging
+
+                logging.getLogger(__name__).warning("peer mapping unavailable (%s): NCCL all-gather instead", e)
+                self.mode = "nccl"
+        if self.mode == "peer":
+            import ctypes
+
+            self._gather = [(ctypes.c_void_p * self.world)(*[p + s * self._slot_bytes for p in self.peers.ptrs]) for s in (0, 1)]
+            self._flags = (ctypes.c_void_p * self.world)(*[p + 2 * self._slot_bytes for p in self.peers.ptrs])
+            self._views = [torch.as_tensor(_DevicePointer(self.peers.ptrs[self.rank] + s * self._slot_bytes, (rows, self.k), "<i8"), device="cuda") for s in (0, 1)]
+            self._error = torch.zeros((1,), dtype=torch.int32, device="cuda")
+        else:
+            self._out = torch.empty((rows, self.k), dtype=torch.int64, device="cuda")
+
+    def step(self):
+        """One sharded query → int64 [n_queries, k] CUDA tensor with every rank's answers (in
+        peer mode a view that stays valid until the call after next)."""
+        from ctypes import c_void_p
+
+        from ._cabi import call
+        from .device import _ptr, stream_ptr
+
+        n_local = self.hi - self.lo
+        if self.mode == "peer":
+            self.epoch += 1
+            slot = self.epoch & 1
+            call("at_knn_query_gather", self.index._h, _ptr(self.q[0]), _ptr(self.q[1]), _ptr(self.q[2]), n_local, self.k, self.ub,
+                 self._gather[slot], self._flags, self.world, self.rank, self.lo, None, None, self.epoch, _ptr(self._error), stream_ptr())  # fmt: skip
+            return self._views[slot][: self.nq]
+        mine = self._out[self.lo : self.lo + n_local]
+        if n_local:
+            call("at_knn_query", self.index._h, _ptr(self.q[0]), _ptr(self.q[1]), _ptr(self.q[2]), n_local, self.k, self.ub, c_void_p(mine.data_ptr()), None, None, stream_ptr())
+        if self.mode == "nccl":
+            _dist().all_gather_into_tensor(self._out, self._out[self.rank * self.per : (self.rank + 1) * self.per])
+        return self._out[: self.nq]
+
+    def timed_out(self) -> bool:
+        return self.mode == "peer" and bool(int(self._error.item()))
+
+    def check_against_single_gpu(self) -> bool:
+        """The gathered result equals what this rank finds when it runs every query itself."""
+        import torch
+
+        got = self.step().clone()
+        torch.cuda.synchronize()
+        full, _, _ = self.index.query(self._all_q, k=self.k, distance_upper_bound=self.ub)
+        return bool(torch.equal(got, full)) and not self.timed_out()
+
+    def describe(self) -> str:
+        return {
+            "local": "single GPU",
+            "peer": "queries split over ranks; the query kernels store their indices into every rank's gather buffer over NVLink peer mappings, one flag-exchange kernel per step (fused compute + all-gather, no NCCL call)",
+            "nccl": "queries split over ranks, written in place into the gather buffer, in-place NCCL all-gather of the int64 indices",
+        }[self.mode]
+
+    def close(self) -> None:
+        if self.peers is not None:
+            self._views = []
+            self.peers.close()
+            self.peers = None
+
+
 # ---- GPU entry points ---------------------------------------------------------------------
 def nearest_grid_points(source_latitudes, source_longitudes, target_latitudes, target_longitudes, max_distance=None, num_neighbours_to_return: int = 1):
     """`spatial.nearest_grid_points` with the target points sharded over the ranks; every
     rank returns the full index array (numpy int64)."""
     from . import spatial
-    from .device import KnnIndex, to_device_f64
+    from .device import KnnIndex
 
     index = KnnIndex(spatial.latlon_to_xyz(source_latitudes, source_longitudes))
     tx = spatial.latlon_to_xyz(np.asarray(target_latitudes), np.asarray(target_longitudes))
     k = int(num_neighbours_to_return)
     ub = float("inf") if max_distance is None else float(max_distance)
 
-    def local(lo: int, hi: int):
-        q = tuple(to_device_f64(a[lo:hi]) for a in tx)
-        return index.query(q, k=k, distance_upper_bound=ub)[0]
-
-    idx = sharded_query(tx[0].shape[0], local)
+    query = ShardedKnnQuery(index, tx, k=k, distance_upper_bound=ub)
+    try:
+        idx = query.step().clone()
+        if query.timed_out():
+            raise RuntimeError("sharded nearest_grid_points: a rank did not deliver its indices")
+    finally:
+        query.close()
     idx = idx[:, 0] if k == 1 else idx
     return idx.cpu().numpy()
 

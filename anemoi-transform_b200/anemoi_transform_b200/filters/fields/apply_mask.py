@@ -150,4 +150,5 @@ class MaskVariable(Filter):
 def device_field_flat(batch, col, template, **metadata):
     from ...fields import new_field_from_device_column
 
+    batch, col = batch.locate(col)
     return new_field_from_device_column(batch, col, template=template, shape=None, **metadata)

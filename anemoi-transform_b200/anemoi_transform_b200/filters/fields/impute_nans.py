@@ -29,4 +29,4 @@ class ImputeNaNs(SingleFieldFilter):
 
     def forward_transform_batch(self, fields: list[Any]) -> list[Any]:
         out = run_epilogue(_cabi.EPI_IMPUTE_NAN, fields, [NO_COL] * len(fields), pa=float(self.value))
-        return [new_field_from_device_column(out, i, template=f, shape=None) for i, f in enumerate(fields)]
+        return [new_field_from_device_column(*out.locate(i), template=f, shape=None) for i, f in enumerate(fields)]

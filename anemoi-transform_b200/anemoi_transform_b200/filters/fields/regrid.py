@@ -24,7 +24,8 @@ import numpy as np
 
 from ... import ekd
 from ...batching import fields_to_batch
-from ...device import CsrMatrix, DeviceBatch, gather_rows, require_cuda
+from ... import _cabi
+from ...device import CsrMatrix, DeviceBatch, StreamedRegrid, gather_rows, require_cuda, results_are_host_bound
 from ...fields import new_field_from_device_column, new_field_from_latitudes_longitudes, new_fieldlist_from_list
 from ...filter import Filter
 from . import filter_registry
@@ -33,9 +34,11 @@ LOG = logging.getLogger(__name__)
 
 
 def _free_device_bytes() -> int:
+    """HBM this process can still use, from torch's own counters (cudaMemGetInfo takes tens of
+    milliseconds on a 180 GB device — too slow for every forward call)."""
     torch = require_cuda()
-    free, _ = torch.cuda.mem_get_info()
-    return int(free + torch.cuda.memory_reserved() - torch.cuda.memory_allocated())
+    total = torch.cuda.get_device_properties(torch.cuda.current_device()).total_memory
+    return int(0.95 * total - torch.cuda.memory_allocated())
 
 
 def as_gridspec(grid: Any) -> dict[str, Any] | None:
@@ -103,8 +106,18 @@ class _BatchedInterpolator:
     memory_fraction = 0.4
 
     def regrid_batch(self, fields: list[Any]) -> list[Any]:
-        """All fields in one device pass — or, when the FieldList does not fit in HBM, in
-        sub-batches whose outputs are moved to host memory as soon as they are computed."""
+        """All fields in one device pass.
+
+        Fields that arrive from the host and whose results are headed back to it are *streamed*
+        (`at_hostio_regrid`: staging, H2D, compute and D2H of consecutive chunks overlap; only
+        the results stay in HBM, and not even those when they would not fit).  Anything else —
+        fields already resident, results wanted by the next filter of a pipeline — takes the
+        batch path, in sub-batches whose outputs are moved to host memory as soon as they are
+        computed when the FieldList does not fit in HBM."""
+        from ...fields import device_column_of
+
+        if results_are_host_bound() and all(device_column_of(f) is None for f in fields):
+            return self._regrid_streamed(fields)
         per_field = self.bytes_per_field(fields[0])
         limit = max(4, int(self.memory_fraction * _free_device_bytes() // max(1, per_field)) // 4 * 4)
         if len(fields) <= limit:
@@ -113,8 +126,6 @@ class _BatchedInterpolator:
         out: list[Any] = []
         for i in range(0, len(fields), limit):
             part = self._regrid_resident(fields[i : i + limit])
-            from ...fields import device_column_of
-
             for batch in {id(b): b for b, _ in filter(None, (device_column_of(f) for f in part))}.values():
                 batch.offload()
             out.extend(part)
@@ -127,6 +138,46 @@ class _BatchedInterpolator:
 
     def output_points(self, n_in: int) -> int:
         return n_in
+
+    @staticmethod
+    def _host_values(field: Any) -> np.ndarray:
+        # reshape(-1) instead of flatten=True: no host copy when the field is contiguous
+        v = np.asarray(field.to_numpy()).reshape(-1)
+        if v.dtype != np.float32 and v.dtype != np.float64:
+            v = v.astype(np.float64)
+        return v if v.flags.c_contiguous else np.ascontiguousarray(v)
+
+    def _wrap(self, fields: list[Any], idxs: list[int], result: DeviceBatch, out: list[Any]) -> None:
+        lat, lon = self.output_grid(fields[idxs[0]])
+        for j, i in enumerate(idxs):
+            out[i] = new_field_from_latitudes_longitudes(new_field_from_device_column(result, j, template=fields[i]), latitudes=lat, longitudes=lon)
+
+    def _regrid_streamed(self, fields: list[Any]) -> list[Any]:
+        torch = require_cuda()
+        self.prepare(fields[0])
+        out: list[Any] = [None] * len(fields)
+        values = [self._host_values(f) for f in fields]
+        by_dtype: dict[Any, list[int]] = {}
+        for i, v in enumerate(values):
+            by_dtype.setdefault(v.dtype, []).append(i)
+        for dtype, idxs in by_dtype.items():
+            arrays = [values[i] for i in idxs]
+            n_src = int(arrays[0].size)
+            for i in idxs:
+                if values[i].size != n_src:
+                    raise ValueError(f"field {i} has {values[i].size} points, expected {n_src}")
+            op, csr, index, n_tgt, y_dtype = self.stream_spec(n_src, torch.float32 if dtype == np.float32 else torch.float64)
+            keep = 8 * n_tgt * len(arrays) <= self.memory_fraction * _free_device_bytes()
+            job = StreamedRegrid(op, csr, index, n_tgt, y_dtype, arrays, keep_resident=keep, to_host=True)
+            try:
+                self._wrap(fields, idxs, job.batch, out)  # while the fields stream through the GPU
+            finally:
+                job.join()
+        return out
+
+    def stream_spec(self, n_src: int, x_dtype: Any):
+        """→ (op, csr, device index, n_tgt, result dtype) of `at_hostio_regrid`."""
+        raise NotImplementedError
 
     def _regrid_resident(self, fields: list[Any]) -> list[Any]:
         self.prepare(fields[0])
@@ -142,18 +193,15 @@ class _BatchedInterpolator:
             if col is not None:
                 key = str(col[0].data.dtype)
             else:
-                # reshape(-1) instead of flatten=True: no host copy when the field is contiguous
-                host_values[i] = v = np.asarray(f.to_numpy()).reshape(-1)
+                host_values[i] = v = self._host_values(f)
                 key = "torch.float32" if v.dtype == np.float32 else "torch.float64"
             by_dtype.setdefault(key, []).append(i)
         for _, idxs in by_dtype.items():
             batch = fields_to_batch([fields[i] for i in idxs], host_values=[host_values.get(i) for i in idxs])
             result = self.apply(batch)
-            lat, lon = self.output_grid(fields[idxs[0]])
-            for j, i in enumerate(idxs):
-                out[i] = new_field_from_latitudes_longitudes(
-                    new_field_from_device_column(result, j, template=fields[i]), latitudes=lat, longitudes=lon
-                )
+            if results_are_host_bound():
+                result.prefetch()
+            self._wrap(fields, idxs, result, out)
         return out
 
     def prepare(self, first_field: Any) -> None:
@@ -186,6 +234,9 @@ class MIRMatrix(_BatchedInterpolator):
         if batch.n_points != self.matrix.shape[1]:
             raise ValueError(f"dimension mismatch: matrix has {self.matrix.shape[1]} columns, field has {batch.n_points} points")
         return DeviceBatch(self.matrix.apply(batch.data, n_fields=batch.n_fields), batch.n_fields)
+
+    def stream_spec(self, n_src: int, x_dtype: Any):
+        return _cabi.HOSTIO_SPMM, self.matrix, None, self.matrix.shape[0], self.matrix.result_dtype(x_dtype)
 
     def output_grid(self, field: Any):
         return self.out_grid["latitudes"], self.out_grid["longitudes"]
@@ -228,11 +279,19 @@ class ScipyKDTreeNearestNeighbours(_BatchedInterpolator):
     def output_points(self, n_in: int) -> int:
         return int(np.size(self.out_grid["latitudes"]))
 
-    def apply(self, batch: DeviceBatch) -> DeviceBatch:
-        n_in = (batch.n_points,)
+    def _check_points(self, n_points: int) -> None:
+        n_in = (n_points,)
         assert n_in == np.shape(self.in_grid["latitudes"]), (n_in, np.shape(self.in_grid["latitudes"]))
         assert n_in == np.shape(self.in_grid["longitudes"]), (n_in, np.shape(self.in_grid["longitudes"]))
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        self._check_points(batch.n_points)
         return DeviceBatch(gather_rows(batch.data, self.nearest_grid_points, n_fields=batch.n_fields), batch.n_fields)
+
+    def stream_spec(self, n_src: int, x_dtype: Any):
+        self._check_points(n_src)
+        idx = self.nearest_grid_points.reshape(-1)
+        return _cabi.HOSTIO_GATHER, None, idx, int(idx.shape[0]), x_dtype
 
     def output_grid(self, field: Any):
         return self.out_grid["latitudes"], self.out_grid["longitudes"]
@@ -250,19 +309,34 @@ class MaskedRegrid(_BatchedInterpolator):
             LOG.warning("Check is not supported by MaskedRegrid")
         self.mask = np.load(mask)["mask"]
         self._device_index = None
+        self._index_points = -1
 
-    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+    def _index(self, n_points: int):
+        """The mask as device int64 indices into a field of n_points (numpy's indexing rules)."""
         torch = require_cuda()
-        if self._device_index is None:
+        if self._device_index is None or self._index_points != n_points:
             m = self.mask
             if m.dtype == np.bool_:
-                if m.shape[0] != batch.n_points:
-                    raise IndexError(f"boolean index did not match indexed array along axis 0; size of axis is {batch.n_points} but size of corresponding boolean axis is {m.shape[0]}")
+                if m.shape[0] != n_points:
+                    raise IndexError(f"boolean index did not match indexed array along axis 0; size of axis is {n_points} but size of corresponding boolean axis is {m.shape[0]}")
                 m = np.nonzero(m)[0]
-            m = np.asarray(m).astype(np.int64)
-            m = np.where(m < 0, m + batch.n_points, m)  # numpy's negative indexing
-            self._device_index = torch.from_numpy(m).cuda()
-        return DeviceBatch(gather_rows(batch.data, self._device_index, n_fields=batch.n_fields), batch.n_fields)
+            m = np.asarray(m).astype(np.int64).reshape(-1)
+            bad = m[(m < -n_points) | (m >= n_points)]
+            if bad.size:
+                raise IndexError(f"index {int(bad[0])} is out of bounds for axis 0 with size {n_points}")
+            m = np.where(m < 0, m + n_points, m)  # numpy's negative indexing
+            self._device_index, self._index_points = torch.from_numpy(m).cuda(), n_points
+        return self._device_index
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        return DeviceBatch(gather_rows(batch.data, self._index(batch.n_points), n_fields=batch.n_fields), batch.n_fields)
+
+    def output_points(self, n_in: int) -> int:
+        return int(self._index(n_in).shape[0])
+
+    def stream_spec(self, n_src: int, x_dtype: Any):
+        idx = self._index(n_src)
+        return _cabi.HOSTIO_GATHER, None, idx, int(idx.shape[0]), x_dtype
 
     def output_grid(self, field: Any):
         if self.out_latitudes is None or self.out_longitudes is None:

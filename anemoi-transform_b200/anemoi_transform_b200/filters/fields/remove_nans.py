@@ -13,7 +13,7 @@ from typing import Any
 
 from ... import _cabi
 from ...batching import fields_to_batch
-from ...device import DeviceBatch, compact_mask, compare_mask, gather_rows
+from ...device import DeviceBatch, compact_mask, compare_mask, gather_rows, results_are_host_bound
 from ...fields import new_field_from_device_column, new_field_from_latitudes_longitudes, new_fieldlist_from_list
 from ...filter import Filter
 from . import filter_registry
@@ -60,6 +60,8 @@ class RemoveNaNs(Filter):
         if batch.n_points != self._mask.shape[0]:
             raise IndexError(f"boolean index did not match indexed array along axis 0; size of axis is {batch.n_points} but size of corresponding boolean axis is {self._mask.shape[0]}")
         out = DeviceBatch(gather_rows(batch.data, self._index, n_fields=batch.n_fields), batch.n_fields)
+        if results_are_host_bound():
+            out.prefetch()
         return new_fieldlist_from_list(
             [
                 new_field_from_latitudes_longitudes(

@@ -14,7 +14,7 @@ from collections.abc import Hashable
 from typing import Any
 
 from ...batching import fields_to_batch
-from ...device import DeviceBatch, sum_cols
+from ...device import DeviceBatch, results_are_host_bound, sum_cols
 from ...fields import new_field_from_device_column, new_fieldlist_from_list
 from ...filter import Filter
 from . import filter_registry
@@ -59,6 +59,8 @@ class Sum(Filter):
             n_terms = len(self.params)
             batch = fields_to_batch([f for g in groups for f in g])
             out = DeviceBatch(sum_cols(batch.data, list(range(len(groups) * n_terms)), len(groups), n_terms), len(groups))
+            if results_are_host_bound():
+                out.prefetch()
             for i, g in enumerate(groups):
                 # the reference sums flattened arrays (sum.py:110)
                 result.append(new_field_from_device_column(out, i, template=g[0], shape=None, param=self.output))

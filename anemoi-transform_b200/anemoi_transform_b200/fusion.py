@@ -25,7 +25,7 @@ import numpy as np
 
 from . import _cabi
 from .batching import fields_to_batch
-from .device import DeviceBatch, Epilogue, require_cuda, round_up
+from .device import DeviceBatch, Epilogue, require_cuda, results_are_host_bound, round_up
 from .fields import DeviceColumnField, NewMetadataField, device_column_of, new_field_from_latitudes_longitudes, new_fieldlist_from_list
 from .filter import Filter
 from .grouping import GroupByParam
@@ -399,6 +399,8 @@ class FusedRegrid(Filter):
         out_cols += [col_params(None)] * (round_up(len(out_cols), 4) - len(out_cols))
 
         x = fields_to_batch(in_fields)
+        if x.n_points != csr.shape[1]:
+            raise ValueError(f"dimension mismatch: matrix has {csr.shape[1]} columns, field has {x.n_points} points")
 
         row_mask = None
         if mask_filter is not None:
@@ -418,7 +420,10 @@ class FusedRegrid(Filter):
             y = epi.apply_fused(csr, x.data, row_mask=row_mask)
         finally:
             epi.close()
-        out_batch = DeviceBatch(y, len(out_cols))
+        # the launch writes round_up(len(out_cols), 4) columns; only those bound to a field count
+        out_batch = DeviceBatch(y, max((col for _, col in assign), default=-1) + 1)
+        if results_are_host_bound():
+            out_batch.prefetch_columns(sorted({col for _, col in assign}))
         for s, col in assign:
             s.node._batch, s.node._col = out_batch, col
         placed = {id(s) for s, _ in assign}

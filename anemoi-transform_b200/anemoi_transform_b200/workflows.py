@@ -39,7 +39,13 @@ class Pipeline(Workflow):
         return self._plan
 
     def forward(self, data: Any) -> Any:
-        for f in self.execution_plan():
+        from .device import results_stay_on_device
+
+        plan = self.execution_plan()
+        for f in plan[:-1]:
+            with results_stay_on_device():  # the next filter consumes them in HBM
+                data = f.forward(data)
+        for f in plan[-1:]:
             data = f.forward(data)
         return data
 

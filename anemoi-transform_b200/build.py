@@ -24,7 +24,7 @@ INCLUDE = ROOT / "include"
 LIB_DIR = HERE / "anemoi_transform_b200" / "lib"
 LIB_PATH = LIB_DIR / "libat_b200.so"
 
-SOURCES = ["misc.cu", "spmm.cu", "layout.cu", "knn.cu", "masks.cu", "pipeline.cu"]
+SOURCES = ["misc.cu", "spmm.cu", "layout.cu", "knn.cu", "masks.cu", "pipeline.cu", "hostio.cu", "hostcopy.cpp"]
 
 NVCC_FLAGS = [
     "-gencode",
@@ -52,7 +52,7 @@ def _nvcc() -> str:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [INCLUDE / "at_b200.h"]):
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.cpp")) + list(CSRC.glob("*.h")) + [INCLUDE / "at_b200.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -483,12 +483,22 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
 
 constexpr long long kPending = -1;  // idx_out[q*k] of a query the near search left to the tree search
 
-template <bool CACHE>  // CACHE: k > 1, candidate keys cached in shared memory (knn_one)
+// Gather buffers of the other ranks (P2P-mapped over NVLink), already offset to this rank's slice:
+// the query kernels store every finished index there as well, so the all-gather of a sharded
+// query happens inside the search instead of in a collective after it (at_knn_query_gather).
+constexpr int kMaxPeers = 15;
+struct PeerOut {
+    long long* ptr[kMaxPeers];
+    int n;
+};
+
+// CACHE: k > 1, candidate keys cached in shared memory (knn_one); PEERS: also store to peers
+template <bool CACHE, bool PEERS>
 __global__ void __launch_bounds__(256)
     knn_query_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
                      const double* __restrict__ qz, long long nq, int k, double ub2, int near_levels,
                      long long* __restrict__ idx_out, double* __restrict__ dist_out,
-                     uint8_t* __restrict__ tie_out) {
+                     uint8_t* __restrict__ tie_out, const PeerOut peers) {
     // per-warp candidate cache (k > 1 only; the k = 1 launch passes no shared memory)
     extern __shared__ __align__(16) unsigned char s_cache[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -511,6 +521,8 @@ __global__ void __launch_bounds__(256)
         if (lane < k) {
             idx_out[q * k + lane] = idx;
             if (dist_out != nullptr) dist_out[q * k + lane] = sqrt(d2);
+            if (PEERS)
+                for (int p = 0; p < peers.n; ++p) peers.ptr[p][q * k + lane] = idx;
         }
         if (tie_out != nullptr && lane == 0) tie_out[q] = static_cast<uint8_t>(tie);
     }
@@ -541,7 +553,8 @@ __device__ __forceinline__ double box_min_d2(const KnnDev& d, double h, int cx, 
 __global__ void __launch_bounds__(128)
     knn_tree_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
                     const double* __restrict__ qz, long long nq, int k, double ub2,
-                    long long* __restrict__ idx_out, double* __restrict__ dist_out, uint8_t* __restrict__ tie_out) {
+                    long long* __restrict__ idx_out, double* __restrict__ dist_out, uint8_t* __restrict__ tie_out,
+                    const PeerOut peers) {
     const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (q >= nq || idx_out[q * k] != kPending) return;
     const double x = qx[q], y = qy[q], z = qz[q];
@@ -624,7 +637,9 @@ __global__ void __launch_bounds__(128)
     unsigned tie = 0;
     for (int j = 0; j < k; ++j) {
         const bool have = j < cnt;
-        idx_out[q * k + j] = have ? bi[j] : d.n;
+        const long long found = have ? bi[j] : d.n;
+        idx_out[q * k + j] = found;
+        for (int p = 0; p < peers.n; ++p) peers.ptr[p][q * k + j] = found;
         if (dist_out != nullptr) dist_out[q * k + j] = have ? sqrt(bd[j]) : INFINITY;
         if (have && j > 0 && bd[j] == bd[j - 1]) tie |= 1u;
     }
@@ -899,15 +914,9 @@ static unsigned query_blocks(long long nq) {
     return static_cast<unsigned>(std::max(1ll, std::min(want, cap)));
 }
 
-extern "C" int at_knn_query(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
-                            int64_t nq, int kk, double upper_bound, int64_t* idx_out, double* dist_out,
-                            uint8_t* tie_out, void* stream) {
-    AT_REQUIRE(k != nullptr && qx != nullptr && qy != nullptr && qz != nullptr && idx_out != nullptr,
-               "at_knn_query: null argument");
-    AT_REQUIRE(kk >= 1 && kk <= kMaxK, "at_knn_query: k must be in [1, %d] (k=%d)", kMaxK, kk);
-    AT_REQUIRE(nq >= 0, "at_knn_query: negative query count");
-    AT_REQUIRE(!(upper_bound != upper_bound) && upper_bound >= 0, "at_knn_query: bad distance_upper_bound");
-    if (nq == 0) return AT_OK;
+static int launch_knn_query(const at_knn_t* k, const double* qx, const double* qy, const double* qz, int64_t nq, int kk,
+                            double upper_bound, long long* idx_out, double* dist_out, uint8_t* tie_out,
+                            const PeerOut& peers, cudaStream_t st) {
     const double ub2 = upper_bound * upper_bound;
     // near search: ring 1 of the two finest levels, one warp per query; whatever it cannot
     // decide (queries far from every source) goes to the per-thread tree search
@@ -915,27 +924,160 @@ extern "C" int at_knn_query(const at_knn_t* k, const double* qx, const double* q
     const int near_levels = std::min(2, n_grid);
     // k > 1: 8 warps x kCandCap cached keys (float64 d2 + int32 index) = 48 KB per CTA
     const size_t cache_bytes = kk > 1 ? static_cast<size_t>(8) * kCandCap * (sizeof(double) + sizeof(int)) : 0;
-    if (kk > 1)
-        knn_query_kernel<true><<<query_blocks(nq), 256, cache_bytes, as_stream(stream)>>>(
-            k->dev, qx, qy, qz, nq, kk, ub2, near_levels, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+    const unsigned blocks = query_blocks(nq);
+    if (kk > 1 && peers.n > 0)
+        knn_query_kernel<true, true><<<blocks, 256, cache_bytes, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
+    else if (kk > 1)
+        knn_query_kernel<true, false><<<blocks, 256, cache_bytes, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
+    else if (peers.n > 0)
+        knn_query_kernel<false, true><<<blocks, 256, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
     else
-        knn_query_kernel<false><<<query_blocks(nq), 256, 0, as_stream(stream)>>>(
-            k->dev, qx, qy, qz, nq, kk, ub2, near_levels, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+        knn_query_kernel<false, false><<<blocks, 256, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
     AT_LAUNCH_CHECK("knn_query_kernel");
     const long long tree_blocks = (nq + 127) / 128;
     AT_REQUIRE(tree_blocks < (1ll << 31), "at_knn_query: too many queries");
-    knn_tree_kernel<<<static_cast<unsigned>(tree_blocks), 128, 0, as_stream(stream)>>>(
-        k->dev, qx, qy, qz, nq, kk, ub2, reinterpret_cast<long long*>(idx_out), dist_out, tie_out);
+    knn_tree_kernel<<<static_cast<unsigned>(tree_blocks), 128, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, idx_out, dist_out,
+                                                                       tie_out, peers);
     AT_LAUNCH_CHECK("knn_tree_kernel");
+    return AT_OK;
+}
+
+extern "C" int at_knn_query(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
+                            int64_t nq, int kk, double upper_bound, int64_t* idx_out, double* dist_out,
+                            uint8_t* tie_out, void* stream) {
+    AT_REQUIRE(k != nullptr, "at_knn_query: null index");
+    AT_REQUIRE(kk >= 1 && kk <= kMaxK, "at_knn_query: k must be in [1, %d] (k=%d)", kMaxK, kk);
+    AT_REQUIRE(nq >= 0, "at_knn_query: negative query count");
+    AT_REQUIRE(!(upper_bound != upper_bound) && upper_bound >= 0, "at_knn_query: bad distance_upper_bound");
+    if (nq == 0) return AT_OK;  // an empty query set has null pointers (zero-length device arrays)
+    AT_REQUIRE(qx != nullptr && qy != nullptr && qz != nullptr && idx_out != nullptr, "at_knn_query: null argument");
+    PeerOut none;
+    none.n = 0;
+    return launch_knn_query(k, qx, qy, qz, nq, kk, upper_bound, reinterpret_cast<long long*>(idx_out), dist_out, tie_out, none,
+                            as_stream(stream));
+}
+
+// ---- sharded query with the all-gather fused into the search (NVLink peer stores) --------
+namespace {
+
+struct PeerFlags {
+    unsigned long long* ptr[kMaxPeers + 1];  // flag array (uint64[world]) of every rank, own included
+    int world, rank;
+};
+
+// Thread r tells rank r "rank `rank` has finished epoch `epoch`" (release: the peer stores of the
+// kernels before this one on the stream are visible first), then waits until rank r has said the
+// same to us.  A rank that never arrives trips the timeout instead of hanging the GPU.
+__global__ void peer_signal_wait_kernel(const PeerFlags f, unsigned long long epoch, int* __restrict__ error) {
+    const int r = threadIdx.x;
+    if (r >= f.world) return;
+    __threadfence_system();
+    unsigned long long* theirs = f.ptr[r] + f.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* mine = f.ptr[f.rank] + r;
+    unsigned long long t0, now, seen;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 2000000000ull) {  // 2 s
+            *error = 1;
+            break;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int at_knn_query_gather(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
+                                   int64_t nq_local, int kk, double upper_bound, int64_t* const* gather_bufs,
+                                   uint64_t* const* flag_bufs, int world, int rank, int64_t row_offset,
+                                   double* dist_out, uint8_t* tie_out, uint64_t epoch, int32_t* error_flag,
+                                   void* stream) {
+    AT_REQUIRE(k != nullptr && gather_bufs != nullptr && flag_bufs != nullptr && error_flag != nullptr,
+               "at_knn_query_gather: null argument");
+    AT_REQUIRE(world >= 1 && world <= kMaxPeers + 1 && rank >= 0 && rank < world, "at_knn_query_gather: bad rank %d of %d",
+               rank, world);
+    AT_REQUIRE(kk >= 1 && kk <= kMaxK, "at_knn_query_gather: k must be in [1, %d] (k=%d)", kMaxK, kk);
+    AT_REQUIRE(nq_local >= 0 && row_offset >= 0, "at_knn_query_gather: negative size");
+    AT_REQUIRE(!(upper_bound != upper_bound) && upper_bound >= 0, "at_knn_query_gather: bad distance_upper_bound");
+    for (int r = 0; r < world; ++r)
+        AT_REQUIRE(gather_bufs[r] != nullptr && flag_bufs[r] != nullptr, "at_knn_query_gather: rank %d has no buffer", r);
+    cudaStream_t st = as_stream(stream);
+    if (nq_local > 0) {
+        AT_REQUIRE(qx != nullptr && qy != nullptr && qz != nullptr, "at_knn_query_gather: null queries");
+        PeerOut peers;
+        peers.n = 0;
+        for (int r = 0; r < world; ++r)
+            if (r != rank) peers.ptr[peers.n++] = reinterpret_cast<long long*>(gather_bufs[r]) + row_offset * kk;
+        int rc = launch_knn_query(k, qx, qy, qz, nq_local, kk, upper_bound,
+                                  reinterpret_cast<long long*>(gather_bufs[rank]) + row_offset * kk, dist_out, tie_out, peers, st);
+        if (rc != AT_OK) return rc;
+    }
+    if (world > 1) {
+        PeerFlags f;
+        f.world = world;
+        f.rank = rank;
+        for (int r = 0; r < world; ++r) f.ptr[r] = reinterpret_cast<unsigned long long*>(flag_bufs[r]);
+        peer_signal_wait_kernel<<<1, 32, 0, st>>>(f, epoch, error_flag);
+        AT_LAUNCH_CHECK("peer_signal_wait_kernel");
+    }
+    return AT_OK;
+}
+
+// Device memory another process of this box can map (cudaIpc): the gather buffers and flags of
+// at_knn_query_gather.  Zero-filled.  `handle` receives the 64-byte cudaIpcMemHandle_t.
+extern "C" int at_peer_alloc(size_t bytes, void** ptr, void* handle) {
+    AT_REQUIRE(ptr != nullptr && handle != nullptr && bytes > 0, "at_peer_alloc: bad arguments");
+    *ptr = nullptr;
+    void* p = nullptr;
+    AT_CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        cudaGetLastError();
+        return set_error(AT_ERR_CUDA, "at_peer_alloc: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle, &h, sizeof(h));
+    *ptr = p;
+    return AT_OK;
+}
+
+extern "C" int at_peer_free(void* ptr) {
+    if (ptr != nullptr) AT_CUDA_TRY(cudaFree(ptr));
+    return AT_OK;
+}
+
+// Map a buffer another rank made with at_peer_alloc (enables peer access to its GPU).
+extern "C" int at_peer_open(const void* handle, void** ptr) {
+    AT_REQUIRE(handle != nullptr && ptr != nullptr, "at_peer_open: null argument");
+    *ptr = nullptr;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    cudaError_t e = cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return set_error(AT_ERR_CUDA, "at_peer_open: %s", cudaGetErrorString(e));
+    }
+    return AT_OK;
+}
+
+extern "C" int at_peer_close(void* ptr) {
+    if (ptr != nullptr) AT_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
     return AT_OK;
 }
 
 extern "C" int at_ball_mark(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
                             int64_t nq, double r, uint8_t* mark, void* stream) {
-    AT_REQUIRE(k != nullptr && qx != nullptr && qy != nullptr && qz != nullptr && mark != nullptr,
-               "at_ball_mark: null argument");
+    AT_REQUIRE(k != nullptr, "at_ball_mark: null index");
     AT_REQUIRE(nq >= 0 && r >= 0, "at_ball_mark: bad arguments");
-    if (nq == 0) return AT_OK;
+    if (nq == 0) return AT_OK;  // an empty query set has null pointers (zero-length device arrays)
+    AT_REQUIRE(qx != nullptr && qy != nullptr && qz != nullptr && mark != nullptr, "at_ball_mark: null argument");
     const double r2 = r * r;
     int level = k->dev.n_levels - 1;
     for (int l = 0; l < k->dev.n_levels; ++l) {

@@ -204,9 +204,9 @@ using namespace at;
 
 extern "C" int at_cropping_mask(const double* lats, const double* lons, int64_t n, double north, double west,
                                 double south, double east, uint8_t* mask, void* stream) {
-    AT_REQUIRE(lats != nullptr && lons != nullptr && mask != nullptr, "at_cropping_mask: null argument");
     AT_REQUIRE(n >= 0, "at_cropping_mask: negative size");
-    if (n == 0) return AT_OK;
+    if (n == 0) return AT_OK;  // zero-length device arrays have null pointers
+    AT_REQUIRE(lats != nullptr && lons != nullptr && mask != nullptr, "at_cropping_mask: null argument");
     const int64_t blocks = (n + 255) / 256;
     AT_REQUIRE(blocks < (1ll << 31), "at_cropping_mask: too large");
     // the ±360 bounds are formed on the host in float64 exactly as numpy evaluates west + 360 …
@@ -220,11 +220,11 @@ extern "C" int at_cutout_classify(const double* lx, const double* ly, const doub
                                   const double* gx, const double* gy, const double* gz, int64_t nq,
                                   const int64_t* nbr_idx, const double* nbr_dist, int k, double min_distance,
                                   double max_distance, int dot_mode, uint8_t* out, void* stream) {
-    AT_REQUIRE(lx && ly && lz && gx && gy && gz && nbr_idx && nbr_dist && out, "at_cutout_classify: null argument");
     AT_REQUIRE(k >= 1 && k <= 32, "at_cutout_classify: neighbours must be in [1, 32]");
     AT_REQUIRE(nq >= 0 && n_lam >= 1, "at_cutout_classify: bad sizes");
     AT_REQUIRE(dot_mode == 0 || dot_mode == 1, "at_cutout_classify: dot_mode must be 0 or 1");
-    if (nq == 0) return AT_OK;
+    if (nq == 0) return AT_OK;  // zero-length device arrays have null pointers
+    AT_REQUIRE(lx && ly && lz && gx && gy && gz && nbr_idx && nbr_dist && out, "at_cutout_classify: null argument");
     const int64_t blocks = (nq + 127) / 128;
     AT_REQUIRE(blocks < (1ll << 31), "at_cutout_classify: too large");
     const long long* idx = reinterpret_cast<const long long*>(nbr_idx);
@@ -241,11 +241,11 @@ extern "C" int at_cutout_classify(const double* lx, const double* ly, const doub
 extern "C" int at_outline_classify(const double* x, const double* y, const double* z, int64_t n,
                                    const int64_t* nbr_idx, const double* nbr_dist, int k, int dot_mode, uint8_t* out,
                                    void* stream) {
-    AT_REQUIRE(x && y && z && nbr_idx && nbr_dist && out, "at_outline_classify: null argument");
     AT_REQUIRE(k >= 1 && k <= 32, "at_outline_classify: neighbours must be in [1, 32]");
     AT_REQUIRE(n >= 0, "at_outline_classify: bad size");
     AT_REQUIRE(dot_mode == 0 || dot_mode == 1, "at_outline_classify: dot_mode must be 0 or 1");
     if (n == 0) return AT_OK;
+    AT_REQUIRE(x && y && z && nbr_idx && nbr_dist && out, "at_outline_classify: null argument");
     const int64_t blocks = (n + 127) / 128;
     AT_REQUIRE(blocks < (1ll << 31), "at_outline_classify: too large");
     const long long* idx = reinterpret_cast<const long long*>(nbr_idx);

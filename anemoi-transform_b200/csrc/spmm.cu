@@ -966,10 +966,12 @@ extern "C" int at_epilogue_destroy(at_epilogue_t* e) {
 }
 
 extern "C" int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi, const float* X,
-                             int64_t ldx, float* Y, int64_t ldy, const uint8_t* row_mask,
+                             int64_t n_src, int64_t ldx, float* Y, int64_t ldy, const uint8_t* row_mask,
                              void* stream) {
     AT_REQUIRE(csr != nullptr && epi != nullptr && X != nullptr && Y != nullptr,
                "at_spmm_fused: null argument");
+    AT_REQUIRE(n_src == csr->n_cols, "at_spmm_fused: dimension mismatch: matrix has %lld columns, X has %lld rows",
+               (long long)csr->n_cols, (long long)n_src);
     AT_REQUIRE(csr->data_dtype == AT_F32, "at_spmm_fused: float32 matrices only");
     AT_REQUIRE(ldx % 4 == 0 && ldx >= epi->n_in_cols, "at_spmm_fused: ldx %lld too small or not a multiple of 4",
                (long long)ldx);

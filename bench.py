@@ -6,36 +6,48 @@
 Workload (config 3 of BASELINE.json, the one the metric is quoted on): regrid 0.25°
 (1440x721 = 1,038,240 points) → N320-shaped (542,080 points) with a 4-point bilinear CSR
 matrix, 3120 float32 fields (10 vars x 13 levels x 24 steps).  One *step* = one pass of the
-matrix over the 3120-field batch.  Synthetic data (no network): seeded random fields, a
+matrix over the 3120-field job.  Synthetic data (no network): seeded random fields, a
 locally built bilinear matrix, an N320-shaped reduced Gaussian grid (the real N320 `pl`
 table is not available offline — same point count and density).
 
 One JSON line on stdout (rank 0):
-    value     fields/s with the batch resident in HBM (device-timed, max over ranks)
-    e2e       fields/s through the C-ABI host pipeline (at_pipeline_regrid): pinned HOST
-              buffers in, HOST buffers out, H2D + D2H inside the timed region
-    roofline  algorithmic bytes per launch / measured launch time vs the measured HBM peak
-    cpu_baseline  the oracle's C port of scipy's csr_matvec on all host cores (bounded sample)
-    knn       config 2: N320 targets vs 0.25° sources, k=1 (queries sharded over ranks,
-              NCCL all-gather of the indices)
+    value         fields/s with the job resident in HBM (device-timed, max over ranks)
+    e2e           fields/s through the reference-facing plugin call:
+                  create_filter_by_name("regrid", matrix=…).forward(FieldList of ordinary numpy
+                  fields) + to_numpy() of every output — host staging, H2D, kernels and D2H all
+                  inside the timed region
+    e2e_cabi      the same bytes through the bare C-ABI pipeline (at_pipeline_regrid) with
+                  caller-pinned buffers: the PCIe floor the plugin path is measured against
+    pipeline_e2e  config 4 as a FieldList pipeline (regrid | uv_to_ddff | q_to_r | clip |
+                  apply_mask, O1280 → N320-shaped, 12 nnz/row), with the reference's five-pass
+                  CPU chain timed beside it (N = 1)
+    roofline      algorithmic bytes per launch / measured launch time vs the measured HBM peak;
+                  `traffic` is read from the committed ncu export under profiles/
+    cpu_baseline  the reference's CPU path on the box's host cores (bounded sample; three
+                  legs, the fastest reported — benchmarks/cpu_reference.py)
+    knn           config 2: N320 targets vs 0.25° sources, k=1 (queries sharded over ranks, the
+                  indices exchanged over NVLink)
 
-Multi-GPU: one process per GPU (torchrun); fields shard with no collective on the math path,
-every rank regrids its own 3120-field batch of an N x 3120-field job ("scaling": "weak").
+Multi-GPU: one process per GPU (torchrun).  STRONG scaling: the 3120 fields of the one job
+are sharded over the ranks (390-392 per GPU at N = 8), no collective on the math path;
+`weak` repeats the round-1 figure (3120 fields on every GPU) as an extra key.
 
---impl reference times the reference's CPU path (per-field csr_matvec, regrid.py:204-208,
-309-310) on the host cores: the oracle's plain-C restatement of scipy's csr_matvec with
-OpenMP over fields (the reference is pure Python + scipy; nothing to compile into
-oracle/_ref), each step a bounded sample of the same workload.
+--impl reference times the reference's CPU path on the host cores of the box, all of them
+whatever OMP_NUM_THREADS says, on the same job at every N: scipy per field on one thread (as
+the reference runs), scipy `csr @ X` over one process per core, and the oracle's plain-C
+restatement under OpenMP; the fastest is the arm.  Each step is a bounded sample of the job.
 """
 
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import statistics
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 from pathlib import Path
@@ -49,14 +61,23 @@ import numpy as np  # noqa: E402
 
 N_FIELDS = 3120
 WORKLOAD = "regrid 0.25deg (1440x721=1,038,240 pts) -> N320-shaped (542,080 pts), 4-nnz bilinear CSR, 3120 float32 fields"
-# dram__bytes_read.sum + dram__bytes_write.sum of spmm_f32_kernel per launch on this workload,
-# from the `ncu --set full` capture summarised in profiles/ (None until captured).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = 18_984_274_000  # profiles/r01_spmm_ncu.md: 12.237 GB read + 6.747 GB write
-CPU_SAMPLE_FIELDS = 624  # 1/5 of the workload per CPU step
+CPU_SAMPLE_FIELDS = 624  # 1/5 of the job per CPU step
+NCU_EXPORT = REPO / "profiles" / "r02_spmm_ncu_raw.csv"  # `ncu --set full … --page raw --csv` of bench.py --value-only
 
 
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def bench_config(world: int) -> dict:
+    """The `config` object — identical in both arms."""
+    return {
+        "workload": WORKLOAD,
+        "fields_total": N_FIELDS,
+        "layout": "point-major [points x fields] float32 in HBM",
+        "l2": "inputs larger than L2 (X 12.96 GB + Y 6.77 GB per step over all ranks; >= 2.4 GB per rank at N=8), no flush needed",
+        "parallelism": f"the 3120 fields sharded over {world} GPU(s) (strong scaling), no collective on the math path",
+    }
 
 
 def measured_peak_gbs() -> tuple[float, str]:
@@ -69,14 +90,42 @@ def measured_peak_gbs() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes(kernel_substring: str = "spmm_f32_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the SpMM kernel, from the
+    committed `ncu --page raw --csv` export (None when there is no capture)."""
+    if not NCU_EXPORT.exists():
+        return None, None
+    try:
+        with NCU_EXPORT.open(newline="") as fh:
+            rows = list(csv.reader(fh))
+        header = next(r for r in rows if "Kernel Name" in r)
+        units = rows[rows.index(header) + 1]
+        k, rd, wr = header.index("Kernel Name"), header.index("dram__bytes_read.sum"), header.index("dram__bytes_write.sum")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        totals = []
+        for r in rows[rows.index(header) + 2 :]:
+            if len(r) > max(k, rd, wr) and kernel_substring in r[k]:
+                totals.append(float(r[rd].replace(",", "")) * scale.get(units[rd], 1.0) + float(r[wr].replace(",", "")) * scale.get(units[wr], 1.0))
+        if not totals:
+            return None, None
+        return statistics.median(totals), str(NCU_EXPORT.relative_to(REPO))
+    except Exception as e:  # a malformed export must not take the bench down
+        log("ncu export unreadable:", e)
+        return None, None
+
+
 def build_workload():
     from anemoi_transform_b200 import synthetic as syn
 
     t_lat, t_lon = syn.n320_like()
     data, idx, ptr, shape = syn.bilinear_matrix(0.25, t_lat, t_lon)
     n_src_ref = int(np.unique(idx).size)
-    alg_bytes = 4 * N_FIELDS * (n_src_ref + shape[0]) + 8 * data.size + 4 * (shape[0] + 1)
-    return dict(data=data, idx=idx, ptr=ptr, shape=shape, n_src_ref=n_src_ref, alg_bytes=alg_bytes, t_lat=t_lat, t_lon=t_lon)
+    return dict(data=data, idx=idx, ptr=ptr, shape=shape, n_src_ref=n_src_ref, t_lat=t_lat, t_lon=t_lon)
+
+
+def algorithmic_bytes(w, n_fields: int) -> int:
+    """every referenced X row read once, every Y row written once, CSR read once."""
+    return 4 * n_fields * (w["n_src_ref"] + w["shape"][0]) + 8 * int(w["data"].size) + 4 * (w["shape"][0] + 1)
 
 
 class ClockSampler:
@@ -150,57 +199,25 @@ def bind_to_gpu_numa_node(local_rank: int):
     return None
 
 
-def cpu_baseline(w, steps: int = 3) -> dict:
-    """The oracle's C port of the reference's per-field csr_matvec loop, all host threads."""
-    from oracle import spmm as ospmm
-
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal((CPU_SAMPLE_FIELDS, w["shape"][1]), dtype=np.float32)
-    threads = ospmm.c_max_threads()
-    ospmm.c_regrid_fields_f32(w["ptr"], w["idx"], w["data"], x[:threads])  # warm-up
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        ospmm.c_regrid_fields_f32(w["ptr"], w["idx"], w["data"], x)
-        times.append(time.perf_counter() - t0)
-    # the reference exactly as it runs it: scipy, one field at a time, one thread
-    from scipy.sparse import csr_array
-
-    m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
-    m @ x[0]
-    t0 = time.perf_counter()
-    for f in range(16):
-        m @ x[f]
-    scipy_1t = 16 / (time.perf_counter() - t0)
-    return {
-        "value": CPU_SAMPLE_FIELDS / min(times),
-        "unit": "fields/s",
-        "cores": threads,
-        "kind": "port",
-        "sample": f"{CPU_SAMPLE_FIELDS} of the {N_FIELDS} fields per step (same matrix and grids), best of {steps}; C port of scipy csr_matvec, OpenMP over fields, host memory in and out",
-        "scipy_single_thread_fields_per_s": scipy_1t,
-        "host_cpus": os.cpu_count(),
-    }
-
-
+# ------------------------------------------------------------------ reference arm -------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import spmm as ospmm
+    from benchmarks.cpu_reference import ReferenceArm
 
     w = build_workload()
-    rng = np.random.default_rng(0)
-    x = rng.standard_normal((CPU_SAMPLE_FIELDS, w["shape"][1]), dtype=np.float32)
-    threads = ospmm.c_max_threads()
+    arm = ReferenceArm(w, CPU_SAMPLE_FIELDS)
     for _ in range(args.warmup):
-        ospmm.c_regrid_fields_f32(w["ptr"], w["idx"], w["data"], x)
-    t0 = time.perf_counter()
+        arm.step()
+    seconds = fields = 0.0
     for _ in range(args.steps):
-        ospmm.c_regrid_fields_f32(w["ptr"], w["idx"], w["data"], x)
-    dt = time.perf_counter() - t0
-    value = CPU_SAMPLE_FIELDS * args.steps / dt
-    sample = f"each step = {CPU_SAMPLE_FIELDS} of the {N_FIELDS} fields; plain-C port of scipy csr_matvec (the reference's `matrix @ data`, regrid.py:309-310), OpenMP over fields"
+        s, f = arm.step()
+        seconds, fields = seconds + s, fields + f
+    value = fields / seconds
+    info = arm.describe()
+    arm.close()
+    cpu = {"value": value, "unit": "fields/s", **info}
     print(
         json.dumps(
             {
@@ -211,14 +228,14 @@ def run_reference(args):
                 "n_gpus": args.gpus,
                 "steps": args.steps,
                 "warmup": args.warmup,
-                "ms_per_step": dt / args.steps * 1e3,
+                "ms_per_step": seconds / args.steps * 1e3,
                 "higher_is_better": True,
-                "scaling": "weak",
+                "scaling": "strong",
                 "vs_baseline": None,
                 "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "sample_fields_per_step": CPU_SAMPLE_FIELDS},
-                "cpu_baseline": {"value": value, "unit": "fields/s", "cores": threads, "kind": "port", "sample": sample},
+                "config": bench_config(args.gpus),
+                "cpu_baseline": cpu,
                 "e2e": {"value": value, "unit": "fields/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             }
         ),
@@ -226,12 +243,210 @@ def run_reference(args):
     )
 
 
+# ------------------------------------------------------------------ GPU arm -------------
+def cpu_baseline(w) -> dict:
+    from benchmarks.cpu_reference import ReferenceArm
+
+    arm = ReferenceArm(w, CPU_SAMPLE_FIELDS)
+    times = [arm.step() for _ in range(3)]
+    s, f = min(times, key=lambda t: t[0] / t[1])
+    info = arm.describe()
+    arm.close()
+    return {"value": f / s, "unit": "fields/s", **info}
+
+
+def make_fieldlist(values, lat, lon, specs=None):
+    from anemoi_transform_b200 import ekd
+
+    if specs is None:
+        specs = [dict(param="t", levelist=850, step=k) for k in range(len(values))]
+    return ekd.from_source("list-of-dicts", [dict(values=v, latitudes=lat, longitudes=lon, **s) for v, s in zip(values, specs)])
+
+
+def plugin_e2e(w, matrix_path, n_local: int, steps: int, rank: int, barrier, max_over_ranks) -> dict:
+    """FieldList of ordinary (pageable) numpy fields → RegridFilter.forward → to_numpy() of
+    every output.  Each field is its own numpy array, as a decoder would deliver them."""
+    from anemoi_transform_b200 import synthetic as syn
+    from anemoi_transform_b200.device import HostIO
+    from anemoi_transform_b200.filters import create_filter_by_name
+
+    n_tgt, n_src = w["shape"]
+    s_lat, s_lon = syn.regular_latlon(0.25)
+    rng = np.random.default_rng(99 + rank)
+    base = rng.standard_normal((min(64, n_local), n_src), dtype=np.float32)
+    values = [np.array(base[k % base.shape[0]]) for k in range(n_local)]
+    fl = make_fieldlist(values, s_lat, s_lon)
+    regrid = create_filter_by_name("regrid", matrix=matrix_path)
+
+    def once():
+        out = regrid.forward(fl)
+        return [f.to_numpy() for f in out]
+
+    arrays = once()  # warm-up: pins the staging slots and grows the page-locked pool
+    del arrays
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        arrays = None  # the consumer is done with the previous step's results
+        arrays = once()
+    seconds = max_over_ranks(time.perf_counter() - t0) / steps
+    parity = None
+    if rank == 0:
+        from scipy.sparse import csr_array
+
+        m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
+        parity = all(bool(np.array_equal((m @ values[f]).view(np.uint32), arrays[f].view(np.uint32))) for f in (0, n_local // 2, n_local - 1))
+    io = HostIO.get()
+    return {
+        "seconds": seconds,
+        "parity_spot_check": parity,
+        "staging_threads": io.n_threads,
+        "path": "create_filter_by_name('regrid', matrix=...).forward(FieldList of pageable numpy fields) + to_numpy() of every output: "
+        "worker threads stage the fields into pinned slots -> H2D -> pack -> SpMM -> unpack -> D2H straight into the page-locked arrays the caller receives",
+    }
+
+
+def cabi_e2e(csr, w, n_local: int, steps: int, chunk: int, rank: int, world: int, barrier, max_over_ranks) -> dict:
+    """The bare C-ABI pipeline on caller-pinned buffers: what PCIe allows for these bytes."""
+    import psutil
+    import torch
+
+    from anemoi_transform_b200.device import HostPipeline
+
+    n_tgt, n_src = w["shape"]
+    per_field = 4 * (n_src + n_tgt)
+    budget = 0.3 * psutil.virtual_memory().available / max(world, 1)
+    pool = int(max(2 * chunk, min(n_local, budget // per_field)))
+    host_in = torch.empty((pool, n_src), dtype=torch.float32).pin_memory()
+    host_out = torch.empty((pool, n_tgt), dtype=torch.float32).pin_memory()
+    hin = host_in.numpy()
+    rng = np.random.default_rng(5 + rank)
+    hin[: min(64, pool)] = rng.standard_normal((min(64, pool), n_src), dtype=np.float32)
+    for f0 in range(64, pool, 64):
+        hin[f0 : f0 + 64] = hin[: min(64, pool - f0)]
+    fields_in = [hin[f % pool] for f in range(n_local)]
+    fields_out = [host_out.numpy()[f % pool] for f in range(n_local)]
+    pipe = HostPipeline(csr, chunk_fields=chunk)
+    pipe.regrid(fields_in[: 2 * chunk], fields_out[: 2 * chunk])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        pipe.regrid(fields_in, fields_out)
+    torch.cuda.synchronize()
+    seconds = max_over_ranks(time.perf_counter() - t0) / steps
+    pipe.close()
+    return {"seconds": seconds, "host_pool_fields": pool}
+
+
+def pipeline_e2e(steps: int = 2, n_groups: int = 48) -> dict:
+    """Config 4 through the public pipeline API, next to the reference's five-pass CPU chain."""
+    import torch
+
+    from anemoi_transform_b200 import spatial
+    from anemoi_transform_b200 import synthetic as syn
+    from anemoi_transform_b200.device import KnnIndex
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+    from anemoi_transform_b200.source import FieldListSource
+    from benchmarks.cpu_reference import host_cores, pipeline_chain_fields_per_s
+
+    s_lat, s_lon = syn.octahedral(1280)
+    t_lat, t_lon = syn.n320_like()
+    sx, tx = spatial.latlon_to_xyz(s_lat, s_lon), spatial.latlon_to_xyz(t_lat, t_lon)
+    knn = KnnIndex(sx)
+    idx, dist, _ = knn.query(tuple(torch.from_numpy(a).cuda() for a in tx), k=12)
+    d, i, p, shape = syn.knn_matrix(idx.cpu().numpy(), dist.cpu().numpy(), sx[0].size)
+    knn.close()
+    del idx, dist
+    tmp = tempfile.mkdtemp(prefix="at_b200_bench_")
+    path = os.path.join(tmp, "c4.npz")
+    syn.save_regrid_npz(path, d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    n_src = shape[1]
+    levels = [50, 100, 150, 200, 250, 300, 400, 500, 600, 700, 850, 925, 1000]
+    rng = np.random.default_rng(4)
+    base = {k: syn.synthetic_field(k, n_src, s) for s, k in enumerate(("u", "v", "q", "t"))}
+    values, specs = [rng.uniform(0.0, 1.0, n_src).astype(np.float32)], [dict(param="lsm", levelist=0, step=0)]
+    for g in range(n_groups):
+        for k in ("u", "v", "q", "t"):
+            values.append(np.array(base[k]))
+            specs.append(dict(param=k, levelist=levels[g % 13], step=g // 13))
+    fl = make_fieldlist(values, s_lat, s_lon, specs)
+    filters = [
+        F("regrid", matrix=path),
+        F("uv_to_ddff"),
+        F("q_to_r"),
+        F("clip", param="r", minimum=0.0, maximum=100.0),
+        F("apply_mask", mask_param="lsm", threshold=0.5, threshold_operator=">", param=["ws", "r"]),
+    ]
+    pipe = FieldListSource(dataset=fl)
+    for f in filters:
+        pipe = pipe | f
+
+    def once():
+        return [f.to_numpy() for f in pipe.forward(None)]
+
+    out = once()
+    fused = bool(getattr(pipe.execution_plan()[1], "last_forward_was_fused", False))
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = None
+        out = once()
+    gpu_s = (time.perf_counter() - t0) / steps
+    n_in = len(values)
+    # the reference's chain on the host: one thread as it runs, and one process per core
+    from scipy.sparse import csr_array
+
+    m = csr_array((d, i, p), shape=shape)
+    group = dict(u=base["u"], v=base["v"], q=base["q"], t=base["t"], level=850, lsm=values[0])
+    as_is = pipeline_chain_fields_per_s(m, [group, group])
+    import multiprocessing as mp
+
+    cores = host_cores()
+    _CHAIN["m"], _CHAIN["group"] = m, group
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_chain_worker, range(cores))
+        t0 = time.perf_counter()
+        pool.map(_chain_worker, range(cores))
+        best_effort = cores * 9 / (time.perf_counter() - t0)
+    return {
+        "workload": f"config 4: regrid O1280 (6,599,680 pts) -> N320-shaped, 12 nnz/row | uv_to_ddff | q_to_r | clip(r) | apply_mask(lsm > 0.5 on ws, r); {n_in} float32 fields in ({n_groups} x u,v,q,t + lsm), {len(out)} out",
+        "value": n_in / gpu_s,
+        "unit": "input fields/s",
+        "ms_per_step": gpu_s * 1e3,
+        "fused_single_launch": fused,
+        "h2d_bytes_per_step": 4 * n_in * n_src,
+        "d2h_bytes_per_step": 4 * len(out) * shape[0],
+        "path": "FieldListSource | regrid | uv_to_ddff | q_to_r | clip | apply_mask -> Pipeline.forward -> to_numpy() of every output (ordinary numpy fields in)",
+        "cpu_chain": {
+            "as_is_fields_per_s": as_is,
+            "as_is_cores": 1,
+            "best_effort_fields_per_s": best_effort,
+            "best_effort_cores": cores,
+            "what": "the reference's five passes (scipy csr @ x per field, numpy wind / humidity formulas per pair, np.clip, mask) — one thread as it runs, and one process per core each running whole groups",
+        },
+        "speedup_vs_as_is": (n_in / gpu_s) / as_is,
+        "speedup_vs_best_effort": (n_in / gpu_s) / best_effort,
+    }
+
+
+_CHAIN: dict = {}
+
+
+def _chain_worker(_):
+    from benchmarks.cpu_reference import pipeline_chain_fields_per_s
+
+    pipeline_chain_fields_per_s(_CHAIN["m"], [_CHAIN["group"], _CHAIN["group"]])
+    return 0
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
 
     from anemoi_transform_b200 import _cabi
-    from anemoi_transform_b200.device import CsrMatrix, HostPipeline, KnnIndex
+    from anemoi_transform_b200 import synthetic as syn
+    from anemoi_transform_b200.device import CsrMatrix, KnnIndex
+    from anemoi_transform_b200.distributed import shard_range
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -257,41 +472,56 @@ def run_gpu(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x: float) -> list[float]:
+        if world == 1:
+            return [x]
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        out = torch.empty((world,), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(out, t)
+        return [float(v) for v in out.cpu()]
+
     w = build_workload()
     n_tgt, n_src = w["shape"]
     csr = CsrMatrix(w["data"], w["idx"], w["ptr"], w["shape"])
+    lo, hi = shard_range(N_FIELDS, rank, world, 4)
+    n_local = hi - lo
 
-    # ---- device-resident: value + roofline -------------------------------------------------
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    X = torch.empty((n_src, N_FIELDS), device=dev, dtype=torch.float32)
-    for c0 in range(0, N_FIELDS, 260):  # fill in slabs: randn of the whole 13 GB would need a second copy
-        X[:, c0 : c0 + 260] = torch.randn((n_src, min(260, N_FIELDS - c0)), device=dev, dtype=torch.float32, generator=gen) * 15.0 + 280.0
-    Y = torch.empty((n_tgt, N_FIELDS), device=dev, dtype=torch.float32)
+    def resident_leg(n_cols: int, sample_clocks: bool):
+        """K launches over an [n_src, n_cols] batch resident in HBM → (ms per step on this rank, clocks, X, Y)."""
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        X = torch.empty((n_src, n_cols), device=dev, dtype=torch.float32)
+        for c0 in range(0, n_cols, 260):  # fill in slabs: randn of the whole batch would need a second copy
+            X[:, c0 : c0 + 260] = torch.randn((n_src, min(260, n_cols - c0)), device=dev, dtype=torch.float32, generator=gen) * 15.0 + 280.0
+        Y = torch.empty((n_tgt, n_cols), device=dev, dtype=torch.float32)
+        sampler = ClockSampler(local_rank) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        for _ in range(args.warmup):
+            csr.apply(X, out=Y, variant=args.variant)
+        if sampler:
+            sampler.wait_for_first_row()
+        barrier()
+        if sampler:
+            sampler.mark()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(args.steps):
+            csr.apply(X, out=Y, variant=args.variant)
+        ev1.record()
+        barrier()
+        if sampler:
+            sampler.mark()
+        clocks = sampler.stop() if sampler else None
+        return ev0.elapsed_time(ev1) / args.steps, clocks, X, Y
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    for _ in range(args.warmup):
-        csr.apply(X, out=Y, variant=args.variant)
-    if rank == 0:
-        sampler.wait_for_first_row()
-    barrier()
-    if rank == 0:
-        sampler.mark()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        csr.apply(X, out=Y, variant=args.variant)
-    ev1.record()
-    barrier()
-    if rank == 0:
-        sampler.mark()
-    clocks = sampler.stop() if rank == 0 else None
-    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    ms_per_step = ms_total / args.steps
-    value = N_FIELDS * world / (ms_per_step * 1e-3)
+    # ---- device-resident, strong scaling: value + roofline ---------------------------------
+    my_ms, clocks, X, Y = resident_leg(n_local, sample_clocks=(rank == 0))
+    per_rank_ms = all_ranks(my_ms)
+    ms_per_step = max(per_rank_ms)
+    value = N_FIELDS / (ms_per_step * 1e-3)
     peak, peak_src = measured_peak_gbs()
-    achieved = w["alg_bytes"] / (ms_per_step * 1e-3) / 1e9
+    alg_local = algorithmic_bytes(w, n_local)
+    achieved = alg_local / (per_rank_ms[0] * 1e-3) / 1e9  # rank 0's kernel: its bytes over its launch time
 
     # parity spot check outside the timed region (rank 0): sampled columns bit-exact vs scipy
     parity = None
@@ -300,9 +530,11 @@ def run_gpu(args):
 
         m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
         parity = True
-        for col in (0, 1777, N_FIELDS - 1):
+        for col in (0, n_local // 2 + 1, n_local - 1):
             ref = m @ X[:, col].cpu().numpy()
             parity = parity and bool(np.array_equal(ref.view(np.uint32), Y[:, col].cpu().numpy().view(np.uint32)))
+    del X, Y
+    torch.cuda.empty_cache()
 
     if args.value_only:
         if rank == 0:
@@ -311,9 +543,18 @@ def run_gpu(args):
             dist.destroy_process_group()
         return
 
+    # ---- weak scaling (round-1 figure): 3120 fields on every GPU ---------------------------
+    weak = None
+    if world > 1:
+        weak_ms, _, X, Y = resident_leg(N_FIELDS, sample_clocks=False)
+        weak_ms = max(all_ranks(weak_ms))
+        weak = {"value": N_FIELDS * world / (weak_ms * 1e-3), "unit": "fields/s", "ms_per_step": weak_ms, "fields_per_gpu": N_FIELDS, "what": "N x 3120-field job, 3120 fields on every GPU"}
+        del X, Y
+        torch.cuda.empty_cache()
+
     # ---- kNN (config 2) ---------------------------------------------------------------------
     from anemoi_transform_b200 import spatial
-    from anemoi_transform_b200 import synthetic as syn
+    from anemoi_transform_b200.distributed import ShardedKnnQuery
 
     s_xyz = spatial.latlon_to_xyz(*syn.regular_latlon(0.25))
     t_xyz = spatial.latlon_to_xyz(w["t_lat"], w["t_lon"])
@@ -322,91 +563,73 @@ def run_gpu(args):
     torch.cuda.synchronize()
     knn_build_ms = (time.perf_counter() - t_build0) * 1e3
     nq = t_xyz[0].shape[0]
-    per = -(-nq // world)
-    lo, hi = min(rank * per, nq), min((rank + 1) * per, nq)
-    q = tuple(torch.from_numpy(a[lo:hi]).to(dev) for a in t_xyz)
-
-    def knn_step():
-        idx, _, _ = knn.query(q, k=1)
-        if world > 1:
-            pad = torch.full((per, 1), -1, dtype=torch.int64, device=dev)
-            pad[: hi - lo] = idx
-            out = torch.empty((world * per, 1), dtype=torch.int64, device=dev)
-            dist.all_gather_into_tensor(out, pad)
-            return out
-        return idx
-
+    sharded = ShardedKnnQuery(knn, t_xyz, k=1)
     for _ in range(3):
-        knn_step()
+        sharded.step()
     barrier()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    knn_iters = 20
+    knn_iters = 50
     k0.record()
     for _ in range(knn_iters):
-        knn_step()
+        sharded.step()
     k1.record()
     barrier()
     knn_ms = max_over_ranks(k0.elapsed_time(k1)) / knn_iters
+    knn_parity = sharded.check_against_single_gpu() if world > 1 else None
     knn_info = {
         "workload": "N320-shaped targets (542,080) vs 0.25deg sources (1,038,240), k=1, float64, exact",
         "queries_per_s": nq / (knn_ms * 1e-3),
         "ms_per_query_batch": knn_ms,
         "build_ms": knn_build_ms,
-        "sharding": "queries split over ranks, NCCL all-gather of int64 indices" if world > 1 else "single GPU",
+        "sharding": sharded.describe(),
+        "gathered_equals_single_gpu": knn_parity,
     }
+    sharded.close()
+    del knn
 
-    # ---- end to end through the C-ABI host pipeline ------------------------------------------
-    del X, Y
-    torch.cuda.empty_cache()
+    # ---- end to end through the plugin call ---------------------------------------------------
+    tmp = tempfile.mkdtemp(prefix="at_b200_bench_")
+    matrix_path = os.path.join(tmp, f"c3_rank{rank}.npz")
+    s_lat, s_lon = syn.regular_latlon(0.25)
+    syn.save_regrid_npz(matrix_path, w["data"], w["idx"], w["ptr"], w["shape"], s_lat, s_lon, w["t_lat"], w["t_lon"])
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    # Pinned host buffers.  Every step moves all 3120 fields in and out over PCIe; when host
-    # memory is short (many ranks on one box) the 3120 field pointers cycle over a smaller
-    # pool of distinct pinned buffers — same bytes copied, smaller host footprint.
-    import psutil
-
-    per_field = 4 * (n_src + n_tgt)
-    budget = 0.6 * psutil.virtual_memory().available / max(world, 1)
-    pool = int(max(2 * args.chunk, min(N_FIELDS, budget // per_field)))
-    host_in = torch.empty((pool, n_src), dtype=torch.float32).pin_memory()
-    host_out = torch.empty((pool, n_tgt), dtype=torch.float32).pin_memory()
-    rng = np.random.default_rng(99 + rank)
-    hin = host_in.numpy()
-    for f0 in range(0, pool, 64):
-        hin[f0 : f0 + 64] = rng.standard_normal((min(64, pool - f0), n_src), dtype=np.float32)
-    fields_in = [hin[f % pool] for f in range(N_FIELDS)]
-    fields_out = [host_out.numpy()[f % pool] for f in range(N_FIELDS)]
-    pipe = HostPipeline(csr, chunk_fields=args.chunk)
-    pipe.regrid(fields_in[: 2 * args.chunk], fields_out[: 2 * args.chunk])  # warm-up
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pipe.regrid(fields_in, fields_out)
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
-    e2e_parity = None
-    if rank == 0:
-        from scipy.sparse import csr_array
-
-        m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
-        e2e_parity = all(bool(np.array_equal((m @ hin[f]).view(np.uint32), host_out.numpy()[f].view(np.uint32))) for f in (0, pool // 2, pool - 1))
-    chunks = -(-N_FIELDS // args.chunk)
+    plug = plugin_e2e(w, matrix_path, n_local, e2e_steps, rank, barrier, max_over_ranks)
+    chunks = -(-n_local // 60)
     e2e = {
-        "value": N_FIELDS * world / e2e_s,
+        "value": N_FIELDS / plug["seconds"],
         "unit": "fields/s",
         "h2d_bytes_per_step": 4 * N_FIELDS * n_src,
         "d2h_bytes_per_step": 4 * N_FIELDS * n_tgt,
         "steps": e2e_steps,
-        "ms_per_step": e2e_s * 1e3,
-        "path": f"at_pipeline_regrid (C-ABI): pinned host fields -> chunked H2D ({args.chunk} fields) -> pack -> SpMM -> unpack -> D2H, 3 streams",
-        "parity_spot_check": e2e_parity,
-        "gpu_launches_per_step": 3 * chunks,
-        "host_pool_fields": pool,
+        "ms_per_step": plug["seconds"] * 1e3,
+        "path": plug["path"],
+        "parity_spot_check": plug["parity_spot_check"],
+        "gpu_launches_per_step": 3 * chunks * world,
+        "staging_threads_per_rank": plug["staging_threads"],
+        "host_gb_per_s": 4 * N_FIELDS * (n_src + n_tgt) / plug["seconds"] / 1e9,
         "numa_node": numa_node,
     }
-    pipe.close()
+    import gc
+
+    gc.collect()
+    cabi = cabi_e2e(csr, w, n_local, max(1, min(2, e2e_steps)), args.chunk, rank, world, barrier, max_over_ranks)
+    e2e_cabi = {
+        "value": N_FIELDS / cabi["seconds"],
+        "unit": "fields/s",
+        "ms_per_step": cabi["seconds"] * 1e3,
+        "path": f"at_pipeline_regrid (C-ABI) on caller-pinned buffers, chunks of {args.chunk} fields, 3 streams: the PCIe floor of these bytes",
+        "host_pool_fields": cabi["host_pool_fields"],
+    }
+
+    pipe4 = None
+    if world == 1 and not args.skip_pipeline:
+        gc.collect()
+        torch.cuda.empty_cache()
+        pipe4 = pipeline_e2e()
 
     if rank == 0:
         base = cpu_baseline(w) if world == 1 else None
+        traffic, traffic_src = ncu_traffic_bytes()
         line = {
             "metric": "regrid_fields_per_s",
             "value": value,
@@ -416,34 +639,35 @@ def run_gpu(args):
             "warmup": args.warmup,
             "ms_per_step": ms_per_step,
             "higher_is_better": True,
-            "scaling": "weak",
+            "scaling": "strong",
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD,
-                "fields_per_gpu": N_FIELDS,
-                "layout": "point-major [points x fields] float32 in HBM",
-                "l2": "inputs larger than L2 (X 12.96 GB + Y 6.77 GB per step), no flush needed",
-                "spmm_variant": args.variant,
-                "parallelism": f"fields sharded over {world} GPU(s), no collective on the math path",
-            },
+            "config": bench_config(world),
+            "fields_per_gpu": [shard_range(N_FIELDS, r, world, 4)[1] - shard_range(N_FIELDS, r, world, 4)[0] for r in range(world)],
+            "per_rank_ms": per_rank_ms,
+            "spmm_variant": args.variant,
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": args.steps,
+            "e2e_cabi": e2e_cabi,
+            "pipeline_e2e": pipe4,
+            "gpu_launches": args.steps * world,
             "roofline": {
                 "bound": "hbm",
                 "achieved": achieved,
                 "peak": peak,
                 "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                "kernel": "spmm_f32_kernel (one launch per step)",
-                "algorithmic_bytes_per_launch": w["alg_bytes"],
+                "traffic": traffic,
+                "traffic_source": traffic_src,
+                "traffic_note": "ncu capture of the N=1 launch (3120 fields)" if traffic else None,
+                "kernel": f"spmm_f32_kernel (one launch per step per GPU, {n_local} fields on rank 0)",
+                "algorithmic_bytes_per_launch": alg_local,
                 "n_src_referenced": w["n_src_ref"],
                 "peak_source": peak_src,
                 "frac_of_8TBs_nominal": achieved / 8000.0,
             },
+            "weak": weak,
             "cpu_baseline": base,
             "knn": knn_info,
             "parity_spot_check": parity,
@@ -470,8 +694,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", type=int, default=0, help="at_spmm kernel shape (0 = default)")
-    ap.add_argument("--chunk", type=int, default=64, help="fields per chunk of the host pipeline")
+    ap.add_argument("--chunk", type=int, default=64, help="fields per chunk of the C-ABI host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--skip-pipeline", action="store_true", help="skip the config-4 pipeline leg")
     ap.add_argument("--value-only", action="store_true", help="device-resident leg only (for ncu captures); prints a partial line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)

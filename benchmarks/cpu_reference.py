@@ -1,0 +1,173 @@
+"""CPU legs of bench.py: the reference's own code path timed on the box's host cores.
+
+Only bench.py's `cpu_baseline` leg and `--impl reference` import this (it executes `oracle/`).
+
+    as_is         the reference exactly as it runs: `csr_array @ x` per field in a Python loop
+                  (filters/fields/regrid.py:204-208, 309-310), one thread — BASELINE.md §2
+                  `cpu_ref_as_is`
+    best_effort   the same scipy arithmetic with a friendlier driver: batched
+                  `csr @ X[points x fields]` (csr_matvecs), fields sharded over one process per
+                  core — BASELINE.md §2 `cpu_best_effort`
+    c_port        oracle/csr_matvec.c (plain-C restatement of scipy's csr_matvec, bitwise equal),
+                  OpenMP over fields, every core
+
+`fastest()` runs all three on a bounded sample and reports the quickest as the arm.
+"""
+
+from __future__ import annotations
+
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+_STATE: dict = {}
+
+
+def host_cores() -> int:
+    """Every core of the box — not OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
+
+
+def _worker_init(data, idx, ptr, shape, fields_per_proc, seed):
+    from scipy.sparse import csr_array
+
+    rng = np.random.default_rng(seed + os.getpid())
+    _STATE["m"] = csr_array((data, idx, ptr), shape=shape)
+    # point-major [n_src, f]: csr_matvecs walks f contiguous values per nonzero
+    _STATE["X"] = rng.standard_normal((shape[1], fields_per_proc), dtype=np.float32)
+    _STATE["m"] @ _STATE["X"][:, :1]  # touch
+
+
+def _worker_step(_):
+    y = _STATE["m"] @ _STATE["X"]
+    return float(y[0, 0])
+
+
+class ScipyProcesses:
+    """`csr @ X` in one process per core; each holds its own shard of fields (host memory)."""
+
+    def __init__(self, w: dict, sample_fields: int, n_procs: int):
+        self.n_procs = max(1, min(n_procs, sample_fields))
+        self.per = max(1, sample_fields // self.n_procs)
+        self.fields = self.per * self.n_procs
+        ctx = mp.get_context("fork")
+        self.pool = ctx.Pool(self.n_procs, initializer=_worker_init, initargs=(w["data"], w["idx"], w["ptr"], tuple(w["shape"]), self.per, 7))
+        self.step()
+
+    def step(self) -> float:
+        t0 = time.perf_counter()
+        self.pool.map(_worker_step, range(self.n_procs), chunksize=1)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def scipy_as_is(w: dict, x_fields: np.ndarray, repeat: int = 3) -> float:
+    """fields/s of the reference's per-field loop on one thread."""
+    from scipy.sparse import csr_array
+
+    m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
+    m @ x_fields[0]
+    best = float("inf")
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        for f in range(x_fields.shape[0]):
+            m @ x_fields[f]
+        best = min(best, time.perf_counter() - t0)
+    return x_fields.shape[0] / best
+
+
+def c_port(w: dict, x_fields: np.ndarray, threads: int, repeat: int = 3) -> float:
+    from oracle import spmm as ospmm
+
+    ospmm.c_regrid_fields_f32(w["ptr"], w["idx"], w["data"], x_fields[: max(1, threads)], n_threads=threads)
+    best = float("inf")
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        ospmm.c_regrid_fields_f32(w["ptr"], w["idx"], w["data"], x_fields, n_threads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return x_fields.shape[0] / best
+
+
+class ReferenceArm:
+    """The three legs on a bounded sample; `step()` runs one timed pass of the fastest."""
+
+    def __init__(self, w: dict, sample_fields: int):
+        self.w, self.cores = w, host_cores()
+        self.sample = sample_fields
+        rng = np.random.default_rng(0)
+        self.x = rng.standard_normal((sample_fields, w["shape"][1]), dtype=np.float32)
+        self.legs: dict[str, float] = {}
+        self.legs["cpu_ref_as_is"] = scipy_as_is(w, self.x[:16], repeat=2)
+        self.legs["c_port_openmp"] = c_port(w, self.x, self.cores, repeat=2)
+        self.procs = ScipyProcesses(w, sample_fields, self.cores)
+        self.legs["cpu_best_effort"] = self.procs.fields / min(self.procs.step() for _ in range(2))
+        self.fastest = max(self.legs, key=self.legs.get)
+
+    def step(self) -> tuple[float, int]:
+        """→ (seconds, fields) of one pass of the fastest leg."""
+        if self.fastest == "cpu_best_effort":
+            return self.procs.step(), self.procs.fields
+        if self.fastest == "c_port_openmp":
+            from oracle import spmm as ospmm
+
+            t0 = time.perf_counter()
+            ospmm.c_regrid_fields_f32(self.w["ptr"], self.w["idx"], self.w["data"], self.x, n_threads=self.cores)
+            return time.perf_counter() - t0, self.sample
+        from scipy.sparse import csr_array
+
+        m = csr_array((self.w["data"], self.w["idx"], self.w["ptr"]), shape=self.w["shape"])
+        t0 = time.perf_counter()
+        for f in range(16):
+            m @ self.x[f]
+        return time.perf_counter() - t0, 16
+
+    def describe(self) -> dict:
+        kind = {"cpu_ref_as_is": "reference", "cpu_best_effort": "reference", "c_port_openmp": "port"}[self.fastest]
+        what = {
+            "cpu_ref_as_is": "scipy csr_array @ x per field, one thread (the reference as it runs, regrid.py:204-208, 309-310)",
+            "cpu_best_effort": f"scipy csr_array @ X[points x fields] (csr_matvecs), fields sharded over {self.procs.n_procs} processes (BASELINE.md §2 cpu_best_effort)",
+            "c_port_openmp": "oracle/csr_matvec.c (plain-C restatement of scipy csr_matvec), OpenMP over fields",
+        }[self.fastest]
+        return {
+            "kind": kind,
+            "cores": 1 if self.fastest == "cpu_ref_as_is" else self.cores,
+            "leg": self.fastest,
+            "sample": f"{self.sample} of the 3120 fields per step (same matrix and grids, host memory in and out); {what}",
+            "legs_fields_per_s": self.legs,
+            "host_cpus": os.cpu_count(),
+        }
+
+    def close(self):
+        self.procs.close()
+
+
+# ---- config 4: the reference's five-pass chain ---------------------------------------------
+def pipeline_chain_fields_per_s(m, groups: list[dict], mask_threshold: float = 0.5) -> float:
+    """regrid | uv_to_ddff | q_to_r | clip | apply_mask as the reference runs it: every filter
+    materialises a new FieldList (workflows/pipeline.py:33-48), one numpy call per field / pair,
+    one thread.  `groups`: dicts of source-grid float32 arrays u, v, q, t (+ level) and one lsm.
+    → input fields per second."""
+    from oracle import pointwise as pw
+
+    n_in = 0
+    t0 = time.perf_counter()
+    lsm = m @ groups[0]["lsm"]
+    mask = lsm > mask_threshold
+    for g in groups:
+        u, v, q, t = (m @ g[k] for k in ("u", "v", "q", "t"))  # regrid: one pass per field
+        ws, wdir = pw.xy_to_polar(u, v)  # uv_to_ddff
+        r = pw.relative_humidity_from_specific_humidity(t, q, 100.0 * g["level"])  # q_to_r (keeps q, t)
+        r = np.clip(r, 0.0, 100.0)  # clip
+        for a in (ws, r):  # apply_mask on flattened copies
+            a = a.flatten()
+            a[mask] = np.nan
+        n_in += 4
+    return (n_in + 1) / (time.perf_counter() - t0)

@@ -15,7 +15,7 @@
  *   - "host" / "device" in a parameter comment says where the pointer must live;
  *   - device buffers are caller-owned (torch tensors on the Python side); the library
  *     allocates device memory only inside opaque handles (at_csr_t, at_epilogue_t,
- *     at_knn_t, at_pipeline_t), released by the matching *_destroy;
+ *     at_knn_t, at_pipeline_t, at_hostio_t), released by the matching *_destroy;
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
  *   - no torch / numpy types appear in any signature.
  */
@@ -52,6 +52,7 @@ typedef struct at_csr at_csr_t;
 typedef struct at_epilogue at_epilogue_t;
 typedef struct at_knn at_knn_t;
 typedef struct at_pipeline at_pipeline_t;
+typedef struct at_hostio at_hostio_t;
 
 AT_API const char* at_last_error(void);
 AT_API int at_version(void);
@@ -178,7 +179,8 @@ AT_API int at_epilogue_destroy(at_epilogue_t* epi);
 
 /* Y = epilogue(A · X).  f32 only.  row_mask: device uint8[n_rows] or NULL. */
 AT_API int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi,
-                  const float* X, int64_t ldx, float* Y, int64_t ldy,
+                  const float* X, int64_t n_src /* rows of X; must equal the matrix's n_cols */,
+                  int64_t ldx, float* Y, int64_t ldy,
                   const uint8_t* row_mask, void* stream);
 /* Y = epilogue(X) on a resident batch of n_rows points (the standalone pointwise filters).
  * dtype AT_F32 | AT_F64 is the type of X and Y (numpy keeps the dtype of the field). */
@@ -239,6 +241,68 @@ AT_API int at_pipeline_destroy(at_pipeline_t* p);
 AT_API int at_pipeline_regrid(at_pipeline_t* p, const float* const* fields_in,
                        float* const* fields_out, int64_t n_fields);
 
+/* ------------------------------------------------ field I/O engine (FieldList <-> HBM) --- */
+/*
+ * A caching allocator of page-locked host memory.  The numpy arrays the drop-in filters hand
+ * back to the caller (`field.to_numpy()` of a regridded field, regrid.py:312 wraps a fresh
+ * array per field) are blocks of this pool, so the device-to-host DMA writes the final array.
+ * Blocks are recycled by size; at_pinned_trim returns unused slabs to the system.
+ * AT_B200_PINNED_LIMIT_MB caps the pool (default: half of the physical memory); beyond it
+ * at_pinned_alloc fails with AT_ERR_NOMEM and callers fall back to pageable destinations.
+ */
+AT_API int at_pinned_alloc(size_t bytes, void** out);
+/* n blocks of `bytes` each into out[0..n); all or nothing. */
+AT_API int at_pinned_alloc_many(size_t bytes, int64_t n, void** out);
+AT_API int at_pinned_free(void* ptr);
+AT_API int at_pinned_trim(void);
+AT_API int at_pinned_stats(size_t* bytes_in_use, size_t* bytes_reserved);
+
+/*
+ * The engine: worker threads (n_threads = 0: one per available core, at most 16, or
+ * AT_B200_COPY_THREADS), three pinned + three device staging slots per direction, its own
+ * copy / compute streams.  One engine per device and process is enough.
+ */
+AT_API int at_hostio_create(int32_t n_threads, at_hostio_t** out);
+AT_API int at_hostio_destroy(at_hostio_t* io);
+AT_API int at_hostio_threads(const at_hostio_t* io, int32_t* n_threads, int32_t* nontemporal_copies);
+/*
+ * d_pm[p, f] = fields[f][p]: upload n_fields host arrays of n_points elements (4 or 8 bytes)
+ * into columns [0, n_fields) of a point-major device batch with leading dimension ld.
+ * Replaces: the per-field `field.to_numpy(flatten=True)` hand-over of regrid.py:309 /
+ * matching.py:242-246.  Pageable arrays are staged by the worker threads; page-locked ones
+ * are read in place.  Device work is ordered on `stream`; the call returns when every input
+ * byte has been consumed (the caller may reuse its arrays).
+ */
+AT_API int at_hostio_upload(at_hostio_t* io, const void* const* fields, int64_t n_fields, int64_t n_points,
+                     int elem_size, void* d_pm, int64_t ld, void* stream);
+/*
+ * dst[f][p] = d_pm[p, f] for f < n_fields (after the work already queued on `stream`).
+ * Page-locked destinations (at_pinned_alloc blocks): returns at once, *ticket identifies the
+ * transfer; at_hostio_wait(ticket) blocks until the arrays are complete.  Pageable
+ * destinations: complete on return, *ticket = -1.
+ */
+AT_API int at_hostio_download(at_hostio_t* io, const void* d_pm, int64_t ld, int64_t n_fields, int64_t n_points,
+                       int elem_size, void* const* dst, void* stream, int64_t* ticket);
+AT_API int at_hostio_wait(at_hostio_t* io, int64_t ticket);
+/*
+ * One RegridFilter.forward over host fields (regrid.py:174-208), streamed: chunks of fields
+ * are staged, uploaded, packed, transformed and sent back while the next chunk is staged.
+ *   op = AT_HOSTIO_SPMM    y = csr @ x            (MIRMatrix.__call__, regrid.py:309-310)
+ *   op = AT_HOSTIO_GATHER  y = x[gather_idx]      (regrid.py:380, 420); gather_idx device
+ *                          int64[n_out_points], every entry in [0, n_src)
+ * fields_in[f]: host x_dtype[n_src].  d_Y (optional): device [n_tgt, ldy] point-major batch
+ * that keeps the results resident for the next filter; work on `consumer_stream` queued after
+ * the call sees it complete.  fields_out (optional): host destinations of the result dtype
+ * (numpy's result_type of matrix and field), filled behind *ticket as in at_hostio_download.
+ * Returns when the inputs have been consumed.
+ */
+#define AT_HOSTIO_SPMM 0
+#define AT_HOSTIO_GATHER 1
+AT_API int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, const int64_t* gather_idx,
+                     int64_t n_out_points, const void* const* fields_in, int64_t n_fields, int64_t n_src,
+                     int x_dtype, void* d_Y, int64_t ldy, void* const* fields_out, void* consumer_stream,
+                     int64_t* ticket);
+
 /* --------------------------------------------------------------- kNN / masks -------- */
 /*
  * Build the bucketed search structure over source points (float64 xyz, SoA).
@@ -265,6 +329,30 @@ AT_API int at_knn_destroy(at_knn_t* knn);
 AT_API int at_knn_query(const at_knn_t* knn, const double* qx, const double* qy, const double* qz,
                  int64_t nq, int k, double upper_bound,
                  int64_t* idx_out, double* dist_out, uint8_t* tie_out, void* stream);
+/*
+ * at_knn_query for a query set sharded over the GPUs of one box, with the all-gather of the
+ * indices fused into the search: every rank's query kernels store each finished index into the
+ * gather buffer of EVERY rank (P2P-mapped peer memory over NVLink / NVSwitch) at
+ * [row_offset + q], then a one-warp kernel exchanges arrival flags (release / acquire at system
+ * scope) so that work queued on `stream` after the call sees the complete [n_total, k] result in
+ * gather_bufs[rank].  Replaces query + ncclAllGather (spatial.py:628-632 run by
+ * N ranks).  gather_bufs / flag_bufs: HOST arrays of `world` device pointers (own buffers from
+ * at_peer_alloc, the others' from at_peer_open); flag_bufs[r] is uint64[world], zero at start;
+ * `epoch` increases by one per call on every rank.  A rank that does not arrive within 2 s
+ * sets *error_flag (device int32) instead of hanging.  dist_out / tie_out are local
+ * ([nq_local, k] / [nq_local]) or NULL.  world <= 16.
+ */
+AT_API int at_knn_query_gather(const at_knn_t* knn, const double* qx, const double* qy, const double* qz,
+                        int64_t nq_local, int k, double upper_bound,
+                        int64_t* const* gather_bufs, uint64_t* const* flag_bufs, int world, int rank,
+                        int64_t row_offset, double* dist_out, uint8_t* tie_out, uint64_t epoch,
+                        int32_t* error_flag, void* stream);
+/* Device memory that the other processes of the box can map: zero-filled, `handle` receives the
+ * 64-byte inter-process handle to send to the peers; at_peer_open maps a peer's buffer. */
+AT_API int at_peer_alloc(size_t bytes, void** ptr, void* handle);
+AT_API int at_peer_free(void* ptr);
+AT_API int at_peer_open(const void* handle, void** ptr);
+AT_API int at_peer_close(void* ptr);
 /*
  * mark[j] = 1 for every source j with d²(q, j) <= r·r for some query q (mark is OR-ed into;
  * zero it first).  Replaces: cKDTree.query_ball_point + Python set-union  spatial.py:533-534.
