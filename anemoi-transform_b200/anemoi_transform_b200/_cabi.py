@@ -70,6 +70,7 @@ PROTOTYPES = {
     "at_epilogue_destroy": (c_int, [c_void_p]),
     "at_spmm_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p]),
     "at_pointwise": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    "at_gather_pointwise": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "at_transpose": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "at_gather_rows": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_void_p]),
     "at_gather_cols": (c_int, [c_void_p, c_int32, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
@@ -79,6 +80,7 @@ PROTOTYPES = {
     "at_pipeline_create": (c_int, [c_void_p, c_int32, POINTER(c_void_p)]),
     "at_pipeline_destroy": (c_int, [c_void_p]),
     "at_pipeline_regrid": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), c_int64]),
+    "at_bilinear_matrix": (c_int, [c_double, c_double, c_int64, c_double, c_double, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "at_pinned_alloc": (c_int, [c_size_t, POINTER(c_void_p)]),
     "at_pinned_alloc_many": (c_int, [c_size_t, c_int64, POINTER(c_void_p)]),
     "at_pinned_free": (c_int, [c_void_p]),

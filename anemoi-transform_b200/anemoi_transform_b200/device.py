@@ -195,13 +195,22 @@ class Epilogue:
         except Exception:
             pass
 
-    def apply(self, X, out=None, row_mask=None):
-        """Y = epilogue(X) on a resident point-major batch."""
+    def apply(self, X, out=None, row_mask=None, gather=None):
+        """Y = epilogue(X) on a resident point-major batch — or, with `gather` (device int64
+        indices, every entry a valid row of X), Y[r] = epilogue(X[gather[r]])."""
         torch = _torch()
+        if X.shape[1] < self.n_in_cols:
+            raise ValueError(f"the epilogue reads {self.n_in_cols} input columns, X has {X.shape[1]}")
+        n_rows = X.shape[0] if gather is None else int(gather.shape[0])
         if out is None:
-            out = empty_batch(X.shape[0], self.n_out_cols, X.dtype, X.device)
+            out = empty_batch(n_rows, self.n_out_cols, X.dtype, X.device)
         code = {torch.float32: AT_F32, torch.float64: AT_F64}[X.dtype]
-        call("at_pointwise", self.handle, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, _ptr(row_mask), stream_ptr())
+        if gather is None:
+            call("at_pointwise", self.handle, n_rows, _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, _ptr(row_mask), stream_ptr())
+        else:
+            if gather.dtype != torch.int64 or not gather.is_contiguous():
+                raise ValueError("gather must be a contiguous int64 CUDA tensor")
+            call("at_gather_pointwise", self.handle, _ptr(gather), n_rows, X.shape[0], _ptr(X), X.stride(0), _ptr(out), out.stride(0), code, _ptr(row_mask), stream_ptr())
         return out
 
     def apply_fused(self, csr: CsrMatrix, X, out=None, row_mask=None):

@@ -346,15 +346,68 @@ class MaskedRegrid(_BatchedInterpolator):
         return self.out_latitudes, self.out_longitudes
 
 
-class EarthkitRegrid:
-    """earthkit-regrid's pre-generated matrices (regrid.py:211-259): needs the earthkit-regrid
-    package and its matrix inventory; neither ships with this package."""
+class EarthkitRegrid(_BatchedInterpolator):
+    """The `in_grid` / `out_grid` / `method` recipes (reference regrid.py:211-259).
 
-    def __init__(self, *, in_grid: Any, out_grid: Any, method: str = "linear", check: bool = False) -> None:
-        raise NotImplementedError(
-            "regrid: in_grid/out_grid/method configurations resolve to earthkit-regrid's matrix inventory, "
-            "which is outside this package; pass `matrix=` (make-regrid-file), `mask=` or `method='nearest'`"
-        )
+    The reference hands these to `earthkit.regrid.interpolate`, i.e. to earthkit-regrid's
+    inventory of MIR matrices; neither the package nor the inventory exists offline.  Here the
+    matrix is built locally on the device the first time it is needed and applied like any
+    other (`MIRMatrix` machinery: one SpMM over the whole FieldList):
+
+        method="linear"                      4-point bilinear weights, regular lat-lon sources
+                                             (`regrid_files.make_bilinear_matrix`)
+        method="nearest-neighbour" | "nn"    the nearest source point (`make_knn_matrix`, k = 1)
+
+    (`method="nearest"` is dispatched to `ScipyKDTreeNearestNeighbours`, as in the reference.)
+    The class name is the reference's so that `_interpolator` / configuration dumps read the
+    same; other schemes and non-regular sources raise NotImplementedError and still need a
+    `matrix=` made with MIR.
+    """
+
+    METHODS = ("linear", "nearest-neighbour", "nn")
+
+    def __init__(self, *, in_grid: Any = None, out_grid: Any = None, method: str = "linear", check: bool = False) -> None:
+        if method not in self.METHODS:
+            raise NotImplementedError(f"regrid: method {method!r} is not built locally (have {self.METHODS} and 'nearest'); pass `matrix=`")
+        if out_grid is None:
+            raise ValueError("out_grid is required, but not provided")
+        self.in_gridspec = as_gridspec(in_grid)
+        self.out_gridspec = as_gridspec(out_grid)
+        self.in_grid = as_griddata(in_grid)
+        self.out_grid = as_griddata(out_grid)
+        self.method = method
+        self.matrix: CsrMatrix | None = None
+        if check:
+            LOG.warning("Check is not supported by EarthkitRegrid")
+
+    def prepare(self, first_field: Any) -> None:
+        if self.matrix is not None:
+            return
+        if self.in_grid is None:  # earthkit-regrid reads the grid off the field; so do we
+            self.in_grid = as_griddata(first_field)
+        from ...regrid_files import make_bilinear_matrix, make_knn_matrix
+
+        src = (self.in_grid["latitudes"], self.in_grid["longitudes"])
+        dst = (self.out_grid["latitudes"], self.out_grid["longitudes"])
+        if self.method == "linear":
+            data, indices, indptr, shape = make_bilinear_matrix(*src, *dst)
+        else:
+            data, indices, indptr, shape = make_knn_matrix(*src, *dst, k=1)
+        self.matrix = CsrMatrix(data, indices, indptr, shape)
+
+    def output_points(self, n_in: int) -> int:
+        return int(np.size(self.out_grid["latitudes"]))
+
+    def apply(self, batch: DeviceBatch) -> DeviceBatch:
+        if batch.n_points != self.matrix.shape[1]:
+            raise ValueError(f"dimension mismatch: matrix has {self.matrix.shape[1]} columns, field has {batch.n_points} points")
+        return DeviceBatch(self.matrix.apply(batch.data, n_fields=batch.n_fields), batch.n_fields)
+
+    def stream_spec(self, n_src: int, x_dtype: Any):
+        return _cabi.HOSTIO_SPMM, self.matrix, None, self.matrix.shape[0], self.matrix.result_dtype(x_dtype)
+
+    def output_grid(self, field: Any):
+        return self.out_grid["latitudes"], self.out_grid["longitudes"]
 
 
 def _interpolator(*, method: str | None = None, matrix: str | None = None, mask: str | None = None) -> str:

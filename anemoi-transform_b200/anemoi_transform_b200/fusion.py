@@ -1,5 +1,9 @@
 """Fusing `regrid | uv_to_ddff | q_to_r | clip | apply_mask` into one kernel launch.
 
+(Matrix regrids — from a file or built locally — run `at_spmm_fused`; nearest-neighbour and
+mask regrids run `at_gather_pointwise`, the same epilogue behind a row gather.  Followers:
+wind, humidity, dewpoint, cos/sin -> angle, clip, mask and the one-field conversions.)
+
 In the reference every filter of a pipeline materialises a complete new FieldList
 (`workflows/pipeline.py:33-48`), so a regrid followed by four pointwise filters reads and
 writes every field five times.  `at_spmm_fused` applies the pointwise program in the SpMM
@@ -124,19 +128,30 @@ def _unary_plan(f: Any):
 def is_fusable_follower(f: Any) -> bool:
     from .filters.fields.apply_mask import MaskVariable
     from .filters.fields.clipper import Clipper
+    from .filters.fields.cos_sin_from_rad import CosSinFromRad
+    from .filters.fields.dewpoint import DewPoint
     from .filters.fields.q_to_r import HumidityConversion
     from .filters.fields.uv_to_ddff import WindComponents
 
     f = _unwrap(f)
-    if bool(_direction(f, WindComponents) or _direction(f, HumidityConversion)) or isinstance(f, (Clipper, MaskVariable)):
+    if bool(_direction(f, WindComponents) or _direction(f, HumidityConversion) or _direction(f, DewPoint)) or isinstance(f, (Clipper, MaskVariable)):
+        return True
+    if _direction(f, CosSinFromRad) == "backward":  # forward validates the value range first (cos_sin_from_rad.py:74-77)
         return True
     return _unary_plan(f) is not None
 
 
 def is_fusable_regrid(f: Any) -> bool:
-    from .filters.fields.regrid import MIRMatrix, RegridFilter
+    """A regrid whose interpolator the fused launch can run: a float32 matrix (from a file or
+    built locally) through `at_spmm_fused`, a nearest-neighbour or mask gather through
+    `at_gather_pointwise`."""
+    from .filters.fields.regrid import EarthkitRegrid, MaskedRegrid, MIRMatrix, RegridFilter, ScipyKDTreeNearestNeighbours
 
-    return isinstance(f, RegridFilter) and isinstance(f.interpolator, MIRMatrix) and f.interpolator.matrix.dtype == np.float32
+    if not isinstance(f, RegridFilter):
+        return False
+    if isinstance(f.interpolator, MIRMatrix):
+        return f.interpolator.matrix.dtype == np.float32
+    return isinstance(f.interpolator, (EarthkitRegrid, ScipyKDTreeNearestNeighbours, MaskedRegrid))
 
 
 def flatten(filters: list[Any]) -> list[Any]:
@@ -198,13 +213,16 @@ class FusedRegrid(Filter):
     def _forward_fused(self, fields: list[Any]) -> Any:
         from .filters.fields.apply_mask import MaskVariable
         from .filters.fields.clipper import Clipper
+        from .filters.fields.cos_sin_from_rad import CosSinFromRad
+        from .filters.fields.dewpoint import DewPoint
         from .filters.fields.q_to_r import HumidityConversion
         from .filters.fields.uv_to_ddff import WindComponents
 
         torch = require_cuda()
         interp = self.regrid.interpolator
-        n_tgt = interp.matrix.shape[0]
-        lat, lon = interp.out_grid["latitudes"], interp.out_grid["longitudes"]
+        interp.prepare(fields[0])
+        n_tgt = interp.output_points(int(np.prod(fields[0].shape)))
+        lat, lon = interp.output_grid(fields[0])
 
         for f in fields:
             col = device_column_of(f)
@@ -226,11 +244,11 @@ class FusedRegrid(Filter):
 
         for follower in self.followers:
             f = _unwrap(follower)
-            wind = _direction(f, WindComponents)
-            humid = _direction(f, HumidityConversion)
-            if wind or humid:
-                target = f if isinstance(f, (WindComponents, HumidityConversion)) else f.filter
-                syms = self._plan_matching(target, wind or humid, syms, groups)
+            pair_classes = (WindComponents, HumidityConversion, DewPoint, CosSinFromRad)
+            paired = next((d for d in (_direction(f, c) for c in pair_classes) if d), None)
+            if paired:
+                target = f if isinstance(f, pair_classes) else f.filter
+                syms = self._plan_matching(target, paired, syms, groups)
             elif isinstance(f, Clipper):
                 for s in syms:
                     if f._forward_selection.match(s.field):
@@ -286,6 +304,8 @@ class FusedRegrid(Filter):
 
     def _plan_matching(self, f: Any, direction: str, syms: list[_Sym], groups: list[_Group]) -> list[_Sym]:
         """Mirror MatchingFieldsFilter._run on symbolic fields."""
+        from .filters.fields.cos_sin_from_rad import CosSinFromRad
+        from .filters.fields.dewpoint import DewPoint
         from .filters.fields.uv_to_ddff import WindComponents
 
         names = getattr(f.MATCHING, direction)
@@ -309,6 +329,23 @@ class FusedRegrid(Filter):
                     o.src = ("conv", len(groups), k)
                 groups.append(_Group(kind, [a, b], outs))
                 result.extend(outs)
+            elif isinstance(f, CosSinFromRad):  # backward only: (cos, sin) -> the angle, inputs dropped
+                o = a.transformed(param=f.param)
+                o.src = ("conv", len(groups), 0)
+                groups.append(_Group(_cabi.EPI_ATAN2, [a, b], [o], 1.0, 0.0))
+                result.append(o)
+            elif isinstance(f, DewPoint):
+                forward = direction == "forward"
+                keep = bool(returned)
+                kind = (_cabi.EPI_RT2RTD if keep else _cabi.EPI_RT2D) if forward else (_cabi.EPI_DT2DTR if keep else _cabi.EPI_DT2R)
+                template = a if forward else b  # dewpoint.py: forward wraps relative_humidity, backward temperature
+                o = template.transformed(param=f.dewpoint if forward else f.relative_humidity)
+                o.src = ("conv", len(groups), 2 if keep else 0)
+                if keep:
+                    a.src, b.src = ("conv", len(groups), 0), ("conv", len(groups), 1)
+                    result.extend([a, b])
+                groups.append(_Group(kind, [a, b], [a, b, o] if keep else [o]))
+                result.append(o)
             else:
                 forward = direction == "forward"
                 keep = bool(returned)
@@ -326,9 +363,12 @@ class FusedRegrid(Filter):
 
     # ------------------------------------------------------------------ launch --------
     def _launch(self, fields: list[Any], syms: list[_Sym], groups: list[_Group], mask_filter: Any, mask_sym: _Sym | None) -> Any:
+        torch = require_cuda()
         interp = self.regrid.interpolator
-        csr = interp.matrix
-        OUT_PER_PAIR = {_cabi.EPI_UV2DDFF: 2, _cabi.EPI_DDFF2UV: 2, _cabi.EPI_QT2R: 1, _cabi.EPI_RT2Q: 1, _cabi.EPI_QT2QTR: 3, _cabi.EPI_RT2RTQ: 3}
+        OUT_PER_PAIR = {
+            _cabi.EPI_UV2DDFF: 2, _cabi.EPI_DDFF2UV: 2, _cabi.EPI_QT2R: 1, _cabi.EPI_RT2Q: 1, _cabi.EPI_QT2QTR: 3, _cabi.EPI_RT2RTQ: 3,
+            _cabi.EPI_ATAN2: 1, _cabi.EPI_RT2D: 1, _cabi.EPI_DT2R: 1, _cabi.EPI_RT2RTD: 3, _cabi.EPI_DT2DTR: 3,
+        }  # fmt: skip
 
         # input columns: plain fields first, then the pairs of each conversion kind
         plain = [s for s in syms if s.src[0] == "col"]
@@ -373,8 +413,8 @@ class FusedRegrid(Filter):
                     assign.append((g.outputs[0], out0 + k))
             segments.append((key[0], in0, len(in_fields) - in0, out0, key[1], key[2]))
             out_cols += seg_out
-        for kind in sorted({g.kind for g in groups if g.kind in OUT_PER_PAIR}):
-            same = [g for g in groups if g.kind == kind]
+        for kind, pa, pb in sorted({(g.kind, g.pa, g.pb) for g in groups if g.kind in OUT_PER_PAIR}):
+            same = [g for g in groups if (g.kind, g.pa, g.pb) == (kind, pa, pb)]
             in0, out0 = len(in_fields), len(out_cols)
             out0 = round_up(out0, 4)
             out_cols += [col_params(None)] * (out0 - len(out_cols))
@@ -394,12 +434,15 @@ class FusedRegrid(Filter):
                     seg_out[p * per + slot] = col_params(o)
                     if id(o) in live:
                         assign.append((o, out0 + p * per + slot))
-            segments.append((kind, in0, len(in_fields) - in0, out0))
+            segments.append((kind, in0, len(in_fields) - in0, out0, pa, pb))
             out_cols += seg_out
         out_cols += [col_params(None)] * (round_up(len(out_cols), 4) - len(out_cols))
 
         x = fields_to_batch(in_fields)
-        if x.n_points != csr.shape[1]:
+        # (matrix | None, gather index | None): validates the number of source points as the
+        # stand-alone regrid does (scipy's dimension mismatch, numpy's IndexError)
+        op, csr, index, n_tgt, _ = interp.stream_spec(x.n_points, torch.float32)
+        if csr is not None and x.n_points != csr.shape[1]:
             raise ValueError(f"dimension mismatch: matrix has {csr.shape[1]} columns, field has {x.n_points} points")
 
         row_mask = None
@@ -408,16 +451,19 @@ class FusedRegrid(Filter):
                 row_mask = mask_filter.mask
             else:
                 one = fields_to_batch([fields[mask_sym.inp]])
-                regridded = csr.apply(one.data, n_fields=1)
+                regridded = interp.apply(one).data
                 row_mask = mask_filter._compute_mask(regridded[:, 0])
-            if row_mask is None or int(row_mask.shape[0]) != csr.shape[0]:
+            if row_mask is None or int(row_mask.shape[0]) != n_tgt:
                 have = None if row_mask is None else int(row_mask.shape[0])
-                raise IndexError(f"boolean index did not match indexed array: mask has {have} points, field has {csr.shape[0]}")
+                raise IndexError(f"boolean index did not match indexed array: mask has {have} points, field has {n_tgt}")
             mask_filter.mask = row_mask
 
         epi = Epilogue(segments, out_cols)
         try:
-            y = epi.apply_fused(csr, x.data, row_mask=row_mask)
+            if op == _cabi.HOSTIO_SPMM:
+                y = epi.apply_fused(csr, x.data, row_mask=row_mask)
+            else:
+                y = epi.apply(x.data, row_mask=row_mask, gather=index.contiguous())
         finally:
             epi.close()
         # the launch writes round_up(len(out_cols), 4) columns; only those bound to a field count

@@ -314,6 +314,7 @@ struct PointwiseArgs {
     const uint8_t* __restrict__ row_mask;
     const T* __restrict__ X;
     T* __restrict__ Y;
+    const long long* __restrict__ row_index;  // output row r reads input row row_index[r] (NULL: r)
     size_t ldx, ldy;
     long long n_rows;
     int rows_per_cta;
@@ -354,6 +355,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     const bool any_mask = f.row_mask != nullptr && (tile.flags_any & AT_COL_MASK) != 0;
     const T* xcol = f.X + 4 * static_cast<size_t>(tile.in_vec0 + lane);
     const EpiClip<T> clip = epilogue_prepare_clip<T>(tile, lane, f.cols);
+    // nearest-neighbour / masked regrid fused with the pointwise program: a row gather on the way in
+    const long long* __restrict__ rix = f.row_index;
+    auto src_row = [rix](long long r) { return rix != nullptr ? __ldg(rix + r) : r; };
 
     // one-in / one-out kinds with next to no arithmetic (clip / mask only, affine, impute) are
     // latency-bound copies: kPwRows rows of loads in flight, the small switch inlined once per row
@@ -367,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
             for (int j = 0; j < kPwRows; ++j) {
                 masked[j] = false;
                 if (lr + j < nrows) {
-                    load4(xcol + static_cast<size_t>(r0 + lr + j) * f.ldx, a[j][0], a[j][1], a[j][2], a[j][3]);
+                    load4(xcol + static_cast<size_t>(src_row(r0 + lr + j)) * f.ldx, a[j][0], a[j][1], a[j][2], a[j][3]);
                     if (any_mask) masked[j] = f.row_mask[r0 + lr + j] != 0;
                 }
             }
@@ -382,18 +386,34 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
 
     const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
     if (group >= nrows) return;
-    T n0, n1, n2, n3;
-    bool nmask = false;
-    load4(xcol + static_cast<size_t>(r0 + group) * f.ldx, n0, n1, n2, n3);
-    if (any_mask) nmask = f.row_mask[r0 + group] != 0;
+    // Transcendental kinds: one copy of the epilogue code, kAhead rows of loads in flight behind
+    // it (a rotating register queue).
+    constexpr int kAhead = 1;  // measured: 3 rows ahead spills at the 64-register cap and is slower (uv2ddff 0.88 -> 0.93 ms)
+    T q[kAhead][4];
+    bool qmask[kAhead];
+#pragma unroll
+    for (int j = 0; j < kAhead; ++j) {
+        qmask[j] = false;
+        q[j][0] = q[j][1] = q[j][2] = q[j][3] = T(0);
+        const int lr = group + j * groups;
+        if (lr < nrows) {
+            load4(xcol + static_cast<size_t>(src_row(r0 + lr)) * f.ldx, q[j][0], q[j][1], q[j][2], q[j][3]);
+            if (any_mask) qmask[j] = f.row_mask[r0 + lr] != 0;
+        }
+    }
 #pragma unroll 1
     for (int lr = group; lr < nrows; lr += groups) {
         const long long row = r0 + lr;
-        const T a0 = n0, a1 = n1, a2 = n2, a3 = n3;
-        const bool masked = nmask;
-        if (lr + groups < nrows) {
-            load4(xcol + static_cast<size_t>(row + groups) * f.ldx, n0, n1, n2, n3);
-            if (any_mask) nmask = f.row_mask[row + groups] != 0;
+        const T a0 = q[0][0], a1 = q[0][1], a2 = q[0][2], a3 = q[0][3];
+        const bool masked = qmask[0];
+#pragma unroll
+        for (int j = 0; j + 1 < kAhead; ++j) {
+            q[j][0] = q[j + 1][0], q[j][1] = q[j + 1][1], q[j][2] = q[j + 1][2], q[j][3] = q[j + 1][3];
+            qmask[j] = qmask[j + 1];
+        }
+        if (lr + kAhead * groups < nrows) {
+            load4(xcol + static_cast<size_t>(src_row(row + kAhead * groups)) * f.ldx, q[kAhead - 1][0], q[kAhead - 1][1], q[kAhead - 1][2], q[kAhead - 1][3]);
+            if (any_mask) qmask[kAhead - 1] = f.row_mask[row + kAhead * groups] != 0;
         }
         epilogue_store<T, true, FAM>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
     }
@@ -1034,13 +1054,14 @@ extern "C" int at_spmm_fused(const at_csr_t* csr, const at_epilogue_t* epi, cons
 template <typename T>
 static int launch_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void* X, int64_t ldx, void* Y,
                             int64_t ldy, const typename ColStore<T>::type* cols, const uint8_t* row_mask,
-                            cudaStream_t st) {
+                            const int64_t* row_index, cudaStream_t st) {
     PointwiseArgs<T> f;
     f.tiles = epi->d_tiles;
     f.cols = cols;
     f.row_mask = row_mask;
     f.X = static_cast<const T*>(X);
     f.Y = static_cast<T*>(Y);
+    f.row_index = reinterpret_cast<const long long*>(row_index);
     f.ldx = static_cast<size_t>(ldx);
     f.ldy = static_cast<size_t>(ldy);
     f.n_rows = n_rows;
@@ -1074,6 +1095,29 @@ extern "C" int at_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void
                "at_pointwise: X and Y must be 16-byte aligned");
     if (n_rows == 0) return AT_OK;
     if (dtype == AT_F32)
-        return launch_pointwise<float>(epi, n_rows, X, ldx, Y, ldy, epi->d_cols32, row_mask, as_stream(stream));
-    return launch_pointwise<double>(epi, n_rows, X, ldx, Y, ldy, epi->d_cols64, row_mask, as_stream(stream));
+        return launch_pointwise<float>(epi, n_rows, X, ldx, Y, ldy, epi->d_cols32, row_mask, nullptr, as_stream(stream));
+    return launch_pointwise<double>(epi, n_rows, X, ldx, Y, ldy, epi->d_cols64, row_mask, nullptr, as_stream(stream));
+}
+
+// Y[r, :] = epilogue(X[idx[r], :]): the nearest-neighbour / masked regrid (a row gather,
+// regrid.py:380, 420) fused with the pointwise filters that follow it — one read of the source
+// rows, one write of the results.  The gather copies values exactly (numpy indexing: -0.0 stays
+// -0.0), unlike a one-nonzero-per-row matrix, which would add them to +0.
+extern "C" int at_gather_pointwise(const at_epilogue_t* epi, const int64_t* idx, int64_t n_out, int64_t n_src,
+                                   const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype,
+                                   const uint8_t* row_mask, void* stream) {
+    AT_REQUIRE(epi != nullptr && X != nullptr && Y != nullptr, "at_gather_pointwise: null argument");
+    AT_REQUIRE(n_out >= 0 && n_src >= 0, "at_gather_pointwise: negative size");
+    AT_REQUIRE(dtype == AT_F32 || dtype == AT_F64, "at_gather_pointwise: bad dtype code");
+    AT_REQUIRE(ldx % 4 == 0 && ldx >= epi->n_in_cols, "at_gather_pointwise: ldx %lld too small or not a multiple of 4",
+               (long long)ldx);
+    AT_REQUIRE(ldy % 4 == 0 && ldy >= epi->n_out_cols, "at_gather_pointwise: ldy %lld too small or not a multiple of 4",
+               (long long)ldy);
+    AT_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0,
+               "at_gather_pointwise: X and Y must be 16-byte aligned");
+    if (n_out == 0) return AT_OK;
+    AT_REQUIRE(idx != nullptr, "at_gather_pointwise: null index");
+    if (dtype == AT_F32)
+        return launch_pointwise<float>(epi, n_out, X, ldx, Y, ldy, epi->d_cols32, row_mask, idx, as_stream(stream));
+    return launch_pointwise<double>(epi, n_out, X, ldx, Y, ldy, epi->d_cols64, row_mask, idx, as_stream(stream));
 }

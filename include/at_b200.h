@@ -188,6 +188,14 @@ AT_API int at_pointwise(const at_epilogue_t* epi, int64_t n_rows,
                  const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype,
                  const uint8_t* row_mask, void* stream);
 
+/* Y[r, :] = epilogue(X[idx[r], :]) for r < n_out: the nearest-neighbour / masked regrid
+ * (`data[..., idx]`, regrid.py:380, 420) fused with the pointwise filters after it.
+ * idx: device int64[n_out], every entry in [0, n_src) (validated by the caller: a kNN result
+ * or a checked mask); values are copied exactly, as numpy indexing does. */
+AT_API int at_gather_pointwise(const at_epilogue_t* epi, const int64_t* idx, int64_t n_out, int64_t n_src,
+                        const void* X, int64_t ldx, void* Y, int64_t ldy, int dtype,
+                        const uint8_t* row_mask, void* stream);
+
 /* --------------------------------------------------------------- layout ------------- */
 /*
  * dst[c, r] = src[r, c]: field-major [n_fields, n_points] <-> point-major
@@ -240,6 +248,21 @@ AT_API int at_pipeline_create(const at_csr_t* csr, int32_t chunk_fields, at_pipe
 AT_API int at_pipeline_destroy(at_pipeline_t* p);
 AT_API int at_pipeline_regrid(at_pipeline_t* p, const float* const* fields_in,
                        float* const* fields_out, int64_t n_fields);
+
+/* ---------------------------------------------------------- matrix construction ------ */
+/*
+ * 4-point bilinear interpolation weights from a regular, longitude-periodic lat-lon grid
+ * (row k at latitude lat0 + k*dlat, column i at longitude lon0 + i*dlon, point k*n_lon + i)
+ * to n_tgt arbitrary points: row t of the CSR matrix has the four entries
+ * data_out[4t..4t+3] / indices_out[4t..4t+3], sorted by column, explicit zeros kept
+ * (indptr is 4*t).  Replaces, for this scheme, the external `mir` binary behind
+ * `make-regrid-file` (commands/make-regrid-file.py:142-160) and earthkit-regrid's matrix
+ * inventory (filters/fields/regrid.py:246-255).  float64 arithmetic, unfused, weights rounded
+ * to float32 last: bitwise the numpy restatement oracle/matrix.py.  All pointers device.
+ */
+AT_API int at_bilinear_matrix(double lat0, double dlat, int64_t n_lat, double lon0, double dlon, int64_t n_lon,
+                       const double* tgt_lat, const double* tgt_lon, int64_t n_tgt,
+                       float* data_out, int32_t* indices_out, void* stream);
 
 /* ------------------------------------------------ field I/O engine (FieldList <-> HBM) --- */
 /*
