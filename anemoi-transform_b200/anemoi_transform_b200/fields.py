@@ -1,14 +1,21 @@
-"""Field wrappers — new data / new metadata / new coordinates on top of a template field.
+"""Field overlays: new values, new metadata or new coordinates laid over a template field.
 
-Behaviour follows the reference `fields.py`: `NewDataField` 139-205, `NewLatLonField`
-318-372, `NewMetadataField` 441-535, `GeoMetadata` 208-315, the factories 645-738 and
-`FieldSelection` 767-797.  Outputs of the regrid filter are wrapped exactly as
+What the reference's wrappers do (`fields.py`: `NewDataField` 139-205, `GeoMetadata` 208-315,
+`NewLatLonField` 318-372, `NewMetadataField` 441-535, `NewClonedField` 538-600, factories
+645-738, `FieldSelection` 767-797) is the contract; the implementation here is this package's
+own.  Outputs of the regrid filter are wrapped exactly as
 `NewLatLonField(NewMetadataField(NewDataField(template, array), **md), lat, lon)`
-(regrid.py:312) so downstream consumers see the same metadata / geography.
+(regrid.py:312), so a downstream consumer sees the same metadata and geography.
 
-`DeviceColumnField` is the one addition: a field whose values live in a column of a
-`DeviceBatch` in HBM; `to_numpy()` downloads on demand, and the filters of this package
-recognise it to keep a pipeline device-resident between filters.
+Every overlay is an `_Overlay`: it keeps the field it wraps in `_field` and answers only what
+it changes; anything else is looked up on the wrapped field (`__getattr__`), with a warning for
+names outside the field protocol — the reference logs the same, which is how accidental
+pass-through is noticed.
+
+`DeviceColumnField` is the addition: values that live in a column of a point-major
+`DeviceBatch` in HBM.  `to_numpy()` brings them to the host on demand; the filters of this
+package recognise such fields (`device_column_of`) and keep a pipeline resident between
+filters.
 """
 
 from __future__ import annotations
@@ -24,7 +31,10 @@ LOG = logging.getLogger(__name__)
 
 MISSING_METADATA = object()
 
-_FORWARDED_QUIETLY = ("mars_area", "mars_grid", "to_numpy", "metadata", "shape", "grid_points", "handle")
+#: the field protocol: forwarded to the wrapped field without a word
+_PROTOCOL = frozenset({"to_numpy", "metadata", "shape", "grid_points", "mars_area", "mars_grid", "handle"})
+#: never forwarded: a copy of the wrapped field would silently drop the overlay
+_NOT_FORWARDED = frozenset({"clone", "copy"})
 
 
 def new_fieldlist_from_list(fields: list[Any]) -> SimpleFieldList:
@@ -35,243 +45,238 @@ def new_empty_fieldlist() -> SimpleFieldList:
     return SimpleFieldList([])
 
 
+def _as_requested(values: np.ndarray, flatten: bool, dtype: Any, index: Any) -> np.ndarray:
+    """The `to_numpy(flatten=, dtype=, index=)` options, applied in the reference's order
+    (cast, then flatten — `flatten()` always copies —, then index)."""
+    out = values if dtype is None else values.astype(dtype)
+    if flatten:
+        out = out.flatten()
+    return out if index is None else out[index]
+
+
 class WrappedField:
-    """Forwards everything it does not override to the wrapped field."""
+    """Base of the overlays: holds the wrapped field, forwards what it does not define."""
 
     def __init__(self, field: Any) -> None:
         self._field = field
 
     def __getattr__(self, name: str) -> Any:
-        if name in ("clone", "copy"):
-            raise AttributeError(f"{self}: forwarding of `{name}` is not supported")
-        if name.startswith("__") or name == "_field":
+        # reached only for names the overlay itself does not have
+        if name == "_field" or name.startswith("__"):
             raise AttributeError(name)
-        if name not in _FORWARDED_QUIETLY:
+        if name in _NOT_FORWARDED:
+            raise AttributeError(f"{self}: forwarding of `{name}` is not supported")
+        if name not in _PROTOCOL:
             LOG.warning(f"{self}: forwarding `{name}`")
         return getattr(self._field, name)
 
-    def __repr__(self) -> str:
-        return f"{self.__class__.__name__}({self._field!r}, {self._repr_specific()})"
-
     def _repr_specific(self) -> str:
-        return f"(No specific representation for {self.__class__.__name__})"
+        return f"(No specific representation for {type(self).__name__})"
 
-    def clone(self, **kwargs: Any) -> "NewClonedField":
-        return NewClonedField(self, **kwargs)
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}({self._field!r}, {self._repr_specific()})"
 
     def __iter__(self) -> Any:
         raise NotImplementedError(f"{self}: iterating is not supported")
 
+    def clone(self, **metadata: Any) -> "NewClonedField":
+        return NewClonedField(self, **metadata)
 
-class NewDataField(WrappedField):
-    """Template metadata, new values (a host numpy array owned by the field)."""
+
+_Overlay = WrappedField
+
+
+class NewDataField(_Overlay):
+    """The template's metadata over a host array the field owns."""
 
     def __init__(self, field: Any, data: np.ndarray) -> None:
-        super().__init__(field)
-        self._data = data
-        self.shape = data.shape
+        _Overlay.__init__(self, field)
+        self._data, self.shape = data, data.shape
+
+    def to_numpy(self, flatten: bool = False, dtype: Any = None, index: Any = None) -> np.ndarray:
+        return _as_requested(self._data, flatten, dtype, index)
 
     @property
     def values(self) -> np.ndarray:
         return self.to_numpy(flatten=True)
-
-    def to_numpy(self, flatten: bool = False, dtype: type | None = None, index: Any | None = None) -> np.ndarray:
-        data = self._data
-        if dtype is not None:
-            data = data.astype(dtype)
-        if flatten:
-            data = data.flatten()
-        if index is not None:
-            data = data[index]
-        return data
 
     def _repr_specific(self) -> str:
-        return f"(shape={self._data.shape})"
+        return f"(shape={self.shape})"
 
 
-class DeviceColumnField(WrappedField):
-    """Template metadata, values = column `col` of a point-major `DeviceBatch` in HBM."""
+class DeviceColumnField(_Overlay):
+    """The template's metadata over column `col` of a point-major `DeviceBatch` in HBM."""
 
     def __init__(self, field: Any, batch: Any, col: int, shape: tuple[int, ...] | None = None) -> None:
-        super().__init__(field)
-        self._batch = batch
-        self._col = int(col)
-        self.shape = tuple(shape) if shape is not None else (batch.n_points,)
+        _Overlay.__init__(self, field)
+        self._batch, self._col = batch, int(col)
+        self.shape = (batch.n_points,) if shape is None else tuple(shape)
 
-    @property
-    def batch(self) -> Any:
-        return self._batch
+    batch = property(lambda self: self._batch)
+    column = property(lambda self: self._col)
 
-    @property
-    def column(self) -> int:
-        return self._col
+    def to_numpy(self, flatten: bool = False, dtype: Any = None, index: Any = None) -> np.ndarray:
+        # the batch hands out a fresh host array per call — the caller may write into it, as it
+        # may into the copy the reference's flatten() makes (apply_mask.py:184-185)
+        column = self._batch.take_column(self._col)
+        if dtype is not None:
+            column = column.astype(dtype)
+        if not flatten:
+            column = column.reshape(self.shape)
+        return column if index is None else column[index]
 
     @property
     def values(self) -> np.ndarray:
         return self.to_numpy(flatten=True)
-
-    def to_numpy(self, flatten: bool = False, dtype: type | None = None, index: Any | None = None) -> np.ndarray:
-        # each call hands out a fresh array (reference NewDataField.to_numpy(flatten=True) copies)
-        data = self._batch.take_column(self._col)
-        if dtype is not None:
-            data = data.astype(dtype)
-        if not flatten:
-            data = data.reshape(self.shape)
-        if index is not None:
-            data = data[index]
-        return data
 
     def _repr_specific(self) -> str:
         return f"(device column {self._col} of {self._batch.n_points} points)"
 
 
 class GeoMetadata(Geography):
-    """Geography of a field whose coordinates were replaced."""
+    """Geography of a field whose point coordinates were replaced: latitudes, longitudes, shape
+    and the MARS area are known; a grid description is not (the points are arbitrary)."""
 
     def __init__(self, owner: Any) -> None:
         self.owner = owner
 
+    def _coordinates(self, which: str, dtype: Any) -> np.ndarray:
+        values = getattr(self.owner, which)
+        return values if dtype is None else values.astype(dtype)
+
+    def latitudes(self, dtype: Any = None) -> np.ndarray:
+        return self._coordinates("_latitudes", dtype)
+
+    def longitudes(self, dtype: Any = None) -> np.ndarray:
+        return self._coordinates("_longitudes", dtype)
+
     def shape(self) -> tuple[int, ...]:
         return (len(self.owner._latitudes),)
+
+    def mars_area(self) -> list[float]:
+        lat, lon = self.owner._latitudes, self.owner._longitudes
+        north, south, west, east = np.amax(lat), np.amin(lat), np.amin(lon), np.amax(lon)
+        return [north, west, south, east]
 
     def resolution(self) -> str:
         return "unknown"
 
-    def mars_area(self) -> list[float]:
-        lat, lon = self.owner._latitudes, self.owner._longitudes
-        return [np.amax(lat), np.amin(lon), np.amin(lat), np.amax(lon)]
-
     def mars_grid(self) -> None:
         return None
-
-    def latitudes(self, dtype: type | None = None) -> np.ndarray:
-        return self.owner._latitudes if dtype is None else self.owner._latitudes.astype(dtype)
-
-    def longitudes(self, dtype: type | None = None) -> np.ndarray:
-        return self.owner._longitudes if dtype is None else self.owner._longitudes.astype(dtype)
-
-    def x(self, dtype: type | None = None) -> None:
-        raise NotImplementedError()
-
-    def y(self, dtype: type | None = None) -> None:
-        raise NotImplementedError()
-
-    def _unique_grid_id(self) -> None:
-        raise NotImplementedError()
 
     def projection(self) -> None:
         return None
 
-    def bounding_box(self) -> None:
+    def _undefined(self, *args: Any, **kwargs: Any) -> None:
         raise NotImplementedError()
 
-    def gridspec(self) -> None:
-        raise NotImplementedError()
+    x = y = bounding_box = gridspec = _unique_grid_id = _undefined
 
 
-class NewLatLonField(WrappedField):
-    """Template values and metadata, new point coordinates."""
+class NewLatLonField(_Overlay):
+    """The template's values and metadata at new point coordinates."""
 
     def __init__(self, field: Any, latitudes: np.ndarray, longitudes: np.ndarray) -> None:
-        super().__init__(field)
-        self._latitudes = latitudes
-        self._longitudes = longitudes
+        _Overlay.__init__(self, field)
+        self._latitudes, self._longitudes = latitudes, longitudes
 
     def grid_points(self) -> tuple[np.ndarray, np.ndarray]:
         return self._latitudes, self._longitudes
 
     def to_latlon(self, flatten: bool = True) -> dict[str, np.ndarray]:
         assert flatten
-        return dict(lat=self._latitudes, lon=self._longitudes)
+        return {"lat": self._latitudes, "lon": self._longitudes}
 
     def metadata(self, *args: Any, **kwargs: Any) -> Any:
-        metadata = self._field.metadata(*args, **kwargs)
-        if hasattr(metadata, "geography"):
-            metadata.geography = GeoMetadata(self)
-        return metadata
+        answer = self._field.metadata(*args, **kwargs)
+        if hasattr(answer, "geography"):  # a whole metadata object: its geography is ours now
+            answer.geography = GeoMetadata(self)
+        return answer
 
 
 class _MetadataView:
-    """What `field.metadata()` returns for a field with overridden keys."""
+    """`field.metadata()` of a field with overridden keys: reads go through the overrides,
+    everything else (key listing, `override`) is the wrapped field's."""
 
     def __init__(self, owner: "NewMetadataField") -> None:
         self._owner = owner
-        inner = owner._field.metadata()
-        self.geography = getattr(inner, "geography", None)
+        self._inner = owner._field.metadata()
+        self.geography = getattr(self._inner, "geography", None)
+
+    def _overridden(self, key: str) -> Any:
+        return self._owner.mapping(key, self._owner._field)
+
+    def __getitem__(self, key: str) -> Any:
+        value = self._overridden(key)
+        return self._owner._field.metadata()[key] if value is MISSING_METADATA else value
 
     def get(self, key: str, default: Any = None) -> Any:
-        value = self._owner.mapping(key, self._owner._field)
-        if value is not MISSING_METADATA:
-            return value
-        return self._owner._field.metadata().get(key, default)
+        value = self._overridden(key)
+        return self._owner._field.metadata().get(key, default) if value is MISSING_METADATA else value
 
     def keys(self):
         return self._owner._field.metadata().keys()
-
-    def __getitem__(self, key: str) -> Any:
-        value = self._owner.mapping(key, self._owner._field)
-        if value is not MISSING_METADATA:
-            return value
-        return self._owner._field.metadata()[key]
 
     def override(self, *args: Any, **kwargs: Any) -> Any:
         return self._owner._field.metadata().override(*args, **kwargs)
 
 
-class NewMetadataField(WrappedField):
-    """Template values, selected metadata keys overridden."""
+class NewMetadataField(_Overlay):
+    """The template's values with some metadata keys overridden."""
 
     def __init__(self, field: Any, **kwargs: Any) -> None:
-        super().__init__(field)
+        _Overlay.__init__(self, field)
         self.kwargs = kwargs
 
     def mapping(self, key: str, field: Any) -> Any:
+        """The override for `key`, or MISSING_METADATA (subclasses may compute it)."""
         return self.kwargs.get(key, MISSING_METADATA)
+
+    def _one(self, key: str, **kwargs: Any) -> Any:
+        value = self.mapping(key, self._field)
+        if value is MISSING_METADATA:
+            return self._field.metadata(key, **kwargs)
+        return value(self, key, self._field.metadata()) if callable(value) else value
 
     def metadata(self, *args: Any, **kwargs: Any) -> Any:
         if not args and not kwargs:
             return _MetadataView(self)
         if kwargs.get("namespace"):
-            assert len(args) == 0, (args, kwargs)
-            ns = dict(self._field.metadata(**kwargs))
-            for k in list(ns.keys()):
-                m = self.mapping(k, self._field)
-                if m is not MISSING_METADATA:
-                    ns[k] = m
-            return ns
-
-        def one(key: str) -> Any:
-            value = self.mapping(key, self._field)
-            if value is MISSING_METADATA:
-                return self._field.metadata(key, **kwargs)
-            if callable(value):
-                return value(self, key, self._field.metadata())
-            return value
-
-        result = [one(a) for a in args]
-        return result[0] if len(result) == 1 else tuple(result)
+            assert not args, (args, kwargs)
+            namespace = dict(self._field.metadata(**kwargs))
+            for key in namespace:
+                value = self.mapping(key, self._field)
+                if value is not MISSING_METADATA:
+                    namespace[key] = value
+            return namespace
+        values = tuple(self._one(key, **kwargs) for key in args)
+        return values[0] if len(values) == 1 else values
 
     def _repr_specific(self) -> str:
         return f"(metadata={self.kwargs})"
 
 
-class NewClonedField(WrappedField):
+class NewClonedField(_Overlay):
+    """`field.clone(key=value, …)`: single-key metadata reads answer from the clone's keys
+    (callables are evaluated once, on first use)."""
+
     def __init__(self, field: Any, **metadata: Any) -> None:
-        super().__init__(field)
+        _Overlay.__init__(self, field)
         self._metadata = metadata
 
     def metadata(self, *args: Any, **kwargs: Any) -> Any:
-        if len(args) == 1 and args[0] in self._metadata:
-            value = self._metadata[args[0]]
-            if callable(value):
-                value = self._metadata[args[0]] = value(self._field, args[0], self._field.metadata())
-            return value
-        return self._field.metadata(*args, **kwargs)
+        if len(args) != 1 or args[0] not in self._metadata:
+            return self._field.metadata(*args, **kwargs)
+        key = args[0]
+        if callable(self._metadata[key]):
+            self._metadata[key] = self._metadata[key](self._field, key, self._field.metadata())
+        return self._metadata[key]
 
     def _repr_specific(self) -> str:
         return f"(metadata={self._metadata})"
 
 
+# ---- factories (reference fields.py:645-738) ---------------------------------------------
 def new_field_from_numpy(array: np.ndarray, *, template: Any, **metadata: Any) -> NewMetadataField:
     return NewMetadataField(NewDataField(template, array), **metadata)
 
@@ -291,44 +296,42 @@ def new_field_from_latitudes_longitudes(template: Any, latitudes: np.ndarray, lo
 def device_column_of(field: Any):
     """→ (batch, column) when `field`'s VALUES are a device column, else None.
 
-    Walks through metadata / coordinate wrappers (they do not change values) and stops at
-    the first wrapper that owns data.
-    """
-    f = field
-    while True:
-        if isinstance(f, DeviceColumnField):
+    Metadata and coordinate overlays do not change values, so the walk looks through them and
+    stops at the first overlay that owns data."""
+    node = field
+    while isinstance(node, WrappedField):
+        if isinstance(node, DeviceColumnField):
             # an offloaded batch (DeviceBatch.offload) is a host field again
-            return (f.batch, f.column) if getattr(f.batch, "resident", True) else None
-        if isinstance(f, NewDataField):
+            return (node.batch, node.column) if getattr(node.batch, "resident", True) else None
+        if isinstance(node, NewDataField):
             return None
-        if isinstance(f, WrappedField):
-            f = f._field
-            continue
-        return None
+        node = node._field
+    return None
 
 
 class FieldSelection:
-    """Which fields a single-field filter applies to (keys: param, levelist)."""
+    """Which fields a single-field filter applies to: `param` and / or `levelist`, each a value
+    or a list of values; no key at all selects every field."""
 
     ALLOWED_KEYS = {"param", "levelist"}
 
     def __init__(self, **kwargs: Any):
-        self._spec = kwargs
-        if not set(self._spec).issubset(self.ALLOWED_KEYS):
-            raise ValueError(f"Invalid keys in spec: {tuple(self._spec)} - only {self.ALLOWED_KEYS} are allowed.")
-        for key, value in list(self._spec.items()):
-            if isinstance(value, (str, int, float, bool)):
-                self._spec[key] = (value,)
-            elif value is None or (isinstance(value, (list, tuple)) and len(value) == 0):
-                del self._spec[key]
-            elif not isinstance(value, (list, tuple)):
-                raise ValueError(f"Invalid value for key {key}: {value}")
-        self._all = len(self._spec) == 0
+        unknown = set(kwargs) - self.ALLOWED_KEYS
+        if unknown:
+            raise ValueError(f"Invalid keys in spec: {tuple(kwargs)} - only {self.ALLOWED_KEYS} are allowed.")
+        self._spec: dict[str, tuple] = {}
+        for key, wanted in kwargs.items():
+            if wanted is None or (isinstance(wanted, (list, tuple)) and not wanted):
+                continue  # an absent or empty entry does not restrict
+            if isinstance(wanted, (str, int, float, bool)):
+                wanted = (wanted,)
+            elif not isinstance(wanted, (list, tuple)):
+                raise ValueError(f"Invalid value for key {key}: {wanted}")
+            self._spec[key] = tuple(wanted)
+        self._all = not self._spec
 
     def match(self, field: Any) -> bool:
-        if self._all:
-            return True
         try:
-            return all(field.metadata(key) in values for key, values in self._spec.items())
+            return all(field.metadata(key) in wanted for key, wanted in self._spec.items())
         except KeyError:
             return False

@@ -94,11 +94,13 @@ class SingleFieldFilter(Filter):
     optional_inputs: dict[str, Any] = {}
 
     def __init__(self, **kwargs: Any) -> None:
-        self._config = self.optional_inputs | kwargs
+        # configuration = declared defaults overlaid with what the caller gave
+        self._config = {**self.optional_inputs, **kwargs}
         self._validate_inputs()
         self.prepare_filter()
-        self._forward_selection = FieldSelection(**self.forward_select())
-        self._backward_selection = FieldSelection(**self.backward_select())
+        selections = {"_forward_selection": self.forward_select(), "_backward_selection": self.backward_select()}
+        for attribute, spec in selections.items():
+            setattr(self, attribute, FieldSelection(**spec))
 
     def prepare_filter(self) -> None:
         pass
@@ -119,15 +121,20 @@ class SingleFieldFilter(Filter):
         return new_field_from_numpy(array, template=template, **metadata)
 
     def _validate_inputs(self) -> None:
-        if not self.required_inputs:
+        """The constructor arguments against `required_inputs` / `optional_inputs` (the messages
+        are the reference's, filter.py:165-178: its tests match on them)."""
+        required = self.required_inputs
+        if not required:
             return
-        if not isinstance(self.required_inputs, (list, tuple)):
+        if not isinstance(required, (list, tuple)):
             raise TypeError("Required inputs must be a list or tuple.")
-        if not all(name in self._config for name in self.required_inputs):
-            raise TypeError(f"Missing required input(s): '{set(self.required_inputs) - set(self._config)}'.")
-        leftover = set(self._config) - (set(self.required_inputs) | set(self.optional_inputs))
-        if leftover:
-            raise ValueError(f"Unknown input(s): '{leftover}'.")
+        given = set(self._config)
+        missing = set(required) - given
+        if missing:
+            raise TypeError(f"Missing required input(s): '{missing}'.")
+        unknown = given - set(required) - set(self.optional_inputs)
+        if unknown:
+            raise ValueError(f"Unknown input(s): '{unknown}'.")
 
     @property
     def config(self) -> dict[str, Any]:

@@ -92,7 +92,9 @@ def latlon_to_xyz(lat: NDArray[Any], lon: NDArray[Any], radius: float = 1.0) -> 
     import os
     from concurrent.futures import ThreadPoolExecutor
 
-    workers = max(1, min(8, (len(os.sched_getaffinity(0)) or 2) - 1))
+    # several ranks on one box share its cores
+    local_ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))
+    workers = max(1, min(8, (len(os.sched_getaffinity(0)) or 2) // local_ranks - 1))
     if workers == 1:
         return _latlon_to_xyz_serial(lat, lon, radius)
     if _TRIG_THREADS is None:
@@ -135,6 +137,16 @@ def _query_range(n_q: int, sharded: bool) -> tuple[int, int]:
     from . import distributed as atd
 
     return atd.shard_range(n_q, *atd.world())
+
+
+def _xyz(lats, lons, sharded: bool):
+    """xyz of the points: numpy arrays on the host — or, sharded, device tensors whose host
+    evaluation was split over the ranks (`distributed.latlon_to_xyz_device`)."""
+    if not sharded:
+        return latlon_to_xyz(lats, lons)
+    from . import distributed as atd
+
+    return atd.latlon_to_xyz_device(lats, lons)
 
 
 def _gather_queries(local, n_q: int, sharded: bool):
@@ -203,9 +215,9 @@ def cutout_mask(
 
     mask = cropping_mask(global_lats, global_lons, *_crop_box(lats, lons, effective_cropping_distance))
 
-    global_xyz = latlon_to_xyz(global_lats[mask], global_lons[mask])
-    lam_xyz = latlon_to_xyz(lats, lons)
-    n_lam, n_q = lam_xyz[0].shape[0], global_xyz[0].shape[0]
+    global_xyz = _xyz(global_lats[mask], global_lons[mask], _sharded)
+    lam_xyz = _xyz(lats, lons, _sharded)
+    n_lam, n_q = int(lam_xyz[0].shape[0]), int(global_xyz[0].shape[0])
 
     lam_index = KnnIndex(lam_xyz)
     if isinstance(min_distance_km, (int, float)):
@@ -264,9 +276,9 @@ def thinning_mask(
     _check_latlon_arrays(lats, lons, global_lats, global_lons)
     require_cuda()
     mask = cropping_mask(global_lats, global_lons, *_crop_box(lats, lons, cropping_distance))
-    global_xyz = latlon_to_xyz(global_lats[mask], global_lons[mask])
-    index = KnnIndex(latlon_to_xyz(lats, lons))
-    n_q = global_xyz[0].shape[0]
+    global_xyz = _xyz(global_lats[mask], global_lons[mask], _sharded)
+    index = KnnIndex(_xyz(lats, lons, _sharded))
+    n_q = int(global_xyz[0].shape[0])
     lo, hi = _query_range(n_q, _sharded)
     idx, _, _ = index.query(tuple(a[lo:hi] for a in global_xyz), k=1)
     return _gather_queries(idx[:, 0].contiguous(), n_q, _sharded).cpu().numpy()

@@ -134,23 +134,35 @@ __global__ void bucket_count_kernel(const double* __restrict__ x, const double* 
                                     double oz, double inv_h0, int shift, uint32_t mask,
                                     int32_t* __restrict__ counts, int32_t* __restrict__ bucket_of) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int cx = cell_coord(x[i], ox, inv_h0) >> shift;
-    const int cy = cell_coord(y[i], oy, inv_h0) >> shift;
-    const int cz = cell_coord(z[i], oz, inv_h0) >> shift;
-    const uint32_t b = cell_hash(cx, cy, cz) & mask;
-    bucket_of[i] = static_cast<int32_t>(b);
-    atomicAdd(counts + b, 1);
+    const bool live = i < n;
+    uint32_t b = 0xffffffffu;
+    if (live) {
+        const int cx = cell_coord(x[i], ox, inv_h0) >> shift;
+        const int cy = cell_coord(y[i], oy, inv_h0) >> shift;
+        const int cz = cell_coord(z[i], oz, inv_h0) >> shift;
+        b = cell_hash(cx, cy, cz) & mask;
+        bucket_of[i] = static_cast<int32_t>(b);
+    }
+    // Grid points arrive in spatial order, so the lanes of a warp mostly fall into a handful of
+    // buckets (at the coarse levels: one).  One atomic per distinct bucket per warp instead of
+    // one per point: the coarse levels of a 6.6 M-point build were serialised on 256 counters.
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + b, __popc(peers));
 }
 
 __global__ void bucket_scatter_kernel(const int32_t* __restrict__ bucket_of, long long n,
                                       const int32_t* __restrict__ start, int32_t* __restrict__ cursor,
                                       int32_t* __restrict__ perm) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int b = bucket_of[i];
-    const int slot = atomicAdd(cursor + b, 1);
-    perm[start[b] + slot] = static_cast<int32_t>(i);
+    const bool live = i < n;
+    const int b = live ? bucket_of[i] : -1;
+    // warp-aggregated as in bucket_count_kernel: the leader reserves the group's slots
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (live && lane == leader) base = atomicAdd(cursor + b, __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) perm[start[b] + base + __popc(peers & ((1u << lane) - 1u))] = static_cast<int32_t>(i);
 }
 
 __global__ void permute_points_kernel(const double* __restrict__ x, const double* __restrict__ y,
@@ -550,6 +562,7 @@ __device__ __forceinline__ double box_min_d2(const KnnDev& d, double h, int cx, 
     return (dx * dx + dy * dy + dz * dz) * (1.0 - 1e-10);  // a lower bound despite rounding
 }
 
+template <bool PEERS>
 __global__ void __launch_bounds__(128)
     knn_tree_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
                     const double* __restrict__ qz, long long nq, int k, double ub2,
@@ -639,7 +652,8 @@ __global__ void __launch_bounds__(128)
         const bool have = j < cnt;
         const long long found = have ? bi[j] : d.n;
         idx_out[q * k + j] = found;
-        for (int p = 0; p < peers.n; ++p) peers.ptr[p][q * k + j] = found;
+        if (PEERS)
+            for (int p = 0; p < peers.n; ++p) peers.ptr[p][q * k + j] = found;
         if (dist_out != nullptr) dist_out[q * k + j] = have ? sqrt(bd[j]) : INFINITY;
         if (have && j > 0 && bd[j] == bd[j - 1]) tie |= 1u;
     }
@@ -936,8 +950,10 @@ static int launch_knn_query(const at_knn_t* k, const double* qx, const double* q
     AT_LAUNCH_CHECK("knn_query_kernel");
     const long long tree_blocks = (nq + 127) / 128;
     AT_REQUIRE(tree_blocks < (1ll << 31), "at_knn_query: too many queries");
-    knn_tree_kernel<<<static_cast<unsigned>(tree_blocks), 128, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, idx_out, dist_out,
-                                                                       tie_out, peers);
+    if (peers.n > 0)
+        knn_tree_kernel<true><<<static_cast<unsigned>(tree_blocks), 128, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, idx_out, dist_out, tie_out, peers);
+    else
+        knn_tree_kernel<false><<<static_cast<unsigned>(tree_blocks), 128, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, idx_out, dist_out, tie_out, peers);
     AT_LAUNCH_CHECK("knn_tree_kernel");
     return AT_OK;
 }
