@@ -22,6 +22,7 @@ from .fields import clipper as _clipper  # noqa: E402,F401
 from .fields import cos_sin_from_rad as _cos_sin_from_rad  # noqa: E402,F401
 from .fields import cos_sin_mean_wave_direction as _cos_sin_mwd  # noqa: E402,F401
 from .fields import dewpoint as _dewpoint  # noqa: E402,F401
+from .fields import icon_refinement_level as _icon_refinement_level  # noqa: E402,F401
 from .fields import impute_nans as _impute_nans_fields  # noqa: E402,F401
 from .fields import lnsp_to_sp as _lnsp_to_sp  # noqa: E402,F401
 from .fields import orog_to_z as _orog_to_z  # noqa: E402,F401
@@ -32,6 +33,7 @@ from .fields import rescale as _rescale  # noqa: E402,F401
 from .fields import sum as _sum  # noqa: E402,F401
 from .fields import uv_to_ddff as _uv_to_ddff  # noqa: E402,F401
 from .tabular import assign_to_grid as _assign_to_grid  # noqa: E402,F401
+from .tabular import superob as _superob  # noqa: E402,F401
 
 
 def _merge_registries() -> None:

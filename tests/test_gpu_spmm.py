@@ -173,6 +173,14 @@ def test_layout_kernels(cuda):
             a = rng.normal(size=(rows, cols)).astype(dtype)
             t = transpose(cuda.from_numpy(a).cuda()).cpu().numpy()
             assert np.array_equal(t, a.T)
+        # the 16-byte path (leading dimensions that allow aligned float4 / double2 accesses), with
+        # ragged edges in both directions taken from views of padded arrays
+        for rows, cols, ld_src, ld_dst in ((64, 64, 64, 64), (68, 132, 132, 68), (61, 130, 132, 64), (200, 257, 260, 200), (5, 3, 4, 8), (130, 1000, 1000, 132)):
+            big = cuda.from_numpy(rng.normal(size=(rows, ld_src)).astype(dtype)).cuda()
+            out = cuda.full((cols, ld_dst), -7.0, dtype=big.dtype, device="cuda")
+            transpose(big[:, :cols], out=out[:, :rows])
+            assert cuda.equal(out[:, :rows], big[:, :cols].T.contiguous()), (rows, cols, ld_src, ld_dst)
+            assert bool((out[:, rows:] == -7.0).all())  # nothing written beyond the requested block
         fields = [rng.normal(size=1000).astype(dtype) for _ in range(150)]
         fields[3][7] = np.nan
         b = DeviceBatch.from_host_fields(fields, chunk=64)
