@@ -30,6 +30,7 @@ EPI_OUT_PER_GROUP = {
     EPI_RT2D: 2, EPI_RT2RTD: 6, EPI_DT2R: 2, EPI_DT2DTR: 6,
 }  # fmt: skip
 HOSTIO_SPMM, HOSTIO_GATHER = 0, 1
+EXCHANGE_INLINE, EXCHANGE_BULK = 0, 1
 CMP_NOT_NAN = 6
 COL_CLIP_LO, COL_CLIP_HI, COL_MASK = 1, 2, 4
 
@@ -60,6 +61,7 @@ PROTOTYPES = {
     "at_version": (c_int, []),
     "at_device_count": (c_int, [POINTER(c_int)]),
     "at_set_device": (c_int, [c_int]),
+    "at_device_cache_trim": (c_int, []),
     "at_host_register": (c_int, [c_void_p, c_size_t]),
     "at_host_unregister": (c_int, [c_void_p]),
     "at_csr_create": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, POINTER(c_void_p)]),
@@ -101,7 +103,7 @@ PROTOTYPES = {
     "at_knn_query": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, c_void_p, c_void_p, c_void_p, c_void_p]),
     "at_knn_query_gather": (
         c_int,
-        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_void_p, c_uint64, c_void_p, c_void_p],
+        [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_void_p, c_uint64, c_void_p, c_int, c_void_p],
     ),
     "at_peer_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
     "at_peer_free": (c_int, [c_void_p]),

@@ -488,8 +488,9 @@ class HostIO:
             n = int(os.environ.get("AT_B200_COPY_THREADS", 0))
             local = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
             if n <= 0 and local > 1:
-                # several ranks on one box share its cores (two hardware threads per core assumed)
-                n = max(1, min(8, len(os.sched_getaffinity(0)) // 2 // local))
+                # several ranks on one box share its cores: an equal share each (the native call
+                # runs on a helper thread that stages too; the Python thread mostly waits)
+                n = max(1, min(8, len(os.sched_getaffinity(0)) // local))
             io = cls._engines[dev] = cls(n)  # 0: one staging thread per physical core
         return io
 

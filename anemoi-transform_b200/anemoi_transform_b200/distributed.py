@@ -77,6 +77,28 @@ def all_gather_rows(local, n_total: int):
     return out[:n_total]
 
 
+def all_gather_strided(local, n_total: int):
+    """Inverse of the interleaved split `x[rank::world_size]`: per-rank row blocks → the full
+    [n_total, …] tensor on every rank.  Interleaving spreads queries whose cost depends on
+    where they are (far from every source: a tree walk; near: one bucket ring) evenly over the
+    ranks, which contiguous ranges do not — the cropped global points of config 5 are ordered by
+    latitude and one contiguous eighth of them took 0.07 s where the whole set takes 0.12 s."""
+    import torch
+
+    dist = _dist()
+    rank, ws = world()
+    if ws == 1:
+        return local
+    per = -(-n_total // ws)
+    tail = tuple(local.shape[1:])
+    pad = torch.zeros((per,) + tail, dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((ws * per,) + tail, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad)
+    # out[r * per + j] is item j * ws + r
+    return out.view((ws, per) + tail).transpose(0, 1).reshape((ws * per,) + tail)[:n_total]
+
+
 def all_reduce_or(mask):
     """Element-wise OR of 0/1 uint8 masks across ranks (NCCL has no bitwise OR: MAX on bytes)."""
     dist = _dist()
@@ -171,7 +193,7 @@ class ShardedKnnQuery:
     peer mapping is unavailable the queries write straight into this rank's slice of a
     preallocated buffer and NCCL all-gathers it in place (no per-step allocation either)."""
 
-    def __init__(self, index, qxyz, k: int = 1, distance_upper_bound: float = float("inf"), mode: str = "auto"):
+    def __init__(self, index, qxyz, k: int = 1, distance_upper_bound: float = float("inf"), mode: str = "auto", exchange: str = "bulk"):
         import torch
 
         from .device import to_device_f64
@@ -179,12 +201,15 @@ class ShardedKnnQuery:
         self.index, self.k, self.ub = index, int(k), float(distance_upper_bound)
         self.rank, self.world = world()
         self.nq = int(qxyz[0].shape[0])
-        self.per = -(-self.nq // self.world) if self.nq else 0
-        self.lo, self.hi = shard_range(self.nq, self.rank, self.world)
+        # shards of an even number of queries: every rank's slice of the int64 gather buffer then
+        # starts on a 16-byte boundary (the bulk exchange copies 16 bytes at a time)
+        self.lo, self.hi = shard_range(self.nq, self.rank, self.world, 2)
+        self.per = 2 * -(-(-(-self.nq // 2)) // self.world)  # the stride of shard_range(…, multiple=2)
         self.q = tuple(to_device_f64(a[self.lo : self.hi]) for a in qxyz)
         self._all_q = qxyz
         self.epoch = 0
         self.peers = None
+        self.exchange = exchange
         rows = max(1, self.world * self.per)
         self.mode = "local" if self.world == 1 else mode
         if self.mode in ("auto", "peer"):
@@ -214,7 +239,7 @@ class ShardedKnnQuery:
         peer mode a view that stays valid until the call after next)."""
         from ctypes import c_void_p
 
-        from ._cabi import call
+        from ._cabi import EXCHANGE_BULK, EXCHANGE_INLINE, call
         from .device import _ptr, stream_ptr
 
         n_local = self.hi - self.lo
@@ -222,7 +247,8 @@ class ShardedKnnQuery:
             self.epoch += 1
             slot = self.epoch & 1
             call("at_knn_query_gather", self.index._h, _ptr(self.q[0]), _ptr(self.q[1]), _ptr(self.q[2]), n_local, self.k, self.ub,
-                 self._gather[slot], self._flags, self.world, self.rank, self.lo, None, None, self.epoch, _ptr(self._error), stream_ptr())  # fmt: skip
+                 self._gather[slot], self._flags, self.world, self.rank, self.lo, None, None, self.epoch, _ptr(self._error),
+                 EXCHANGE_BULK if self.exchange == "bulk" else EXCHANGE_INLINE, stream_ptr())  # fmt: skip
             return self._views[slot][: self.nq]
         mine = self._out[self.lo : self.lo + n_local]
         if n_local:
@@ -246,7 +272,9 @@ class ShardedKnnQuery:
     def describe(self) -> str:
         return {
             "local": "single GPU",
-            "peer": "queries split over ranks; the query kernels store their indices into every rank's gather buffer over NVLink peer mappings, one flag-exchange kernel per step (fused compute + all-gather, no NCCL call)",
+            "peer": "queries split over ranks; indices go into every rank's gather buffer over NVLink peer mappings — "
+            + ("one coalesced broadcast kernel after the search whose last CTA exchanges arrival flags" if self.exchange == "bulk" else "stored by the search kernels as each query finishes, then one flag-exchange kernel")
+            + " (no NCCL call, no staging copy)",
             "nccl": "queries split over ranks, written in place into the gather buffer, in-place NCCL all-gather of the int64 indices",
         }[self.mode]
 

@@ -110,6 +110,38 @@ def latlon_to_xyz(lat: NDArray[Any], lon: NDArray[Any], radius: float = 1.0) -> 
     return x, y, z
 
 
+class _Phases:
+    """Wall-clock phases of a spatial function, logged when AT_B200_TIMING is set (each phase is
+    closed with a device synchronisation, so it costs a little; off by default)."""
+
+    def __init__(self, name: str):
+        import os
+
+        self.on = bool(os.environ.get("AT_B200_TIMING"))
+        self.name, self.rows, self.t = name, [], None
+        if self.on:
+            self.mark(None)
+
+    def mark(self, phase: str | None) -> None:
+        if not self.on:
+            return
+        import time
+
+        import torch
+
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        if phase is not None:
+            self.rows.append(f"{phase} {1e3 * (now - self.t):.1f}")
+        self.t = now
+
+    def report(self) -> None:
+        if self.on:
+            import os
+
+            print(f"[{self.name} rank {os.environ.get('RANK', '0')}] " + " | ".join(self.rows) + " ms", flush=True)
+
+
 def _check_latlon_arrays(lats, lons, global_lats, global_lons) -> None:
     assert global_lats.ndim == 1
     assert global_lons.ndim == 1
@@ -131,12 +163,15 @@ def _resolution(points_xyz, sharded: bool = False) -> float:
     return atd.all_reduce_min(index.min_nn_distance(lo, hi - lo), device="cuda")
 
 
-def _query_range(n_q: int, sharded: bool) -> tuple[int, int]:
+def _query_slice(n_q: int, sharded: bool) -> slice:
+    """This rank's share of n_q independent queries: everything, or every world_size-th query
+    (interleaved, so expensive far-away queries and cheap near ones mix on every rank)."""
     if not sharded:
-        return 0, n_q
+        return slice(0, n_q)
     from . import distributed as atd
 
-    return atd.shard_range(n_q, *atd.world())
+    rank, ws = atd.world()
+    return slice(rank, n_q, ws)
 
 
 def _xyz(lats, lons, sharded: bool):
@@ -154,7 +189,7 @@ def _gather_queries(local, n_q: int, sharded: bool):
         return local
     from . import distributed as atd
 
-    return atd.all_gather_rows(local, n_q)
+    return atd.all_gather_strided(local, n_q)
 
 
 def _distance_km_to_resolution(function: str, distance_km, lam_points, global_points) -> float:
@@ -235,16 +270,17 @@ def cutout_mask(
         if neighbours > n_lam:
             # cKDTree pads with index n_lam and the reference then indexes lam_points with it
             raise IndexError(f"index {n_lam} is out of bounds for axis 0 with size {n_lam}")
-        lo, hi = _query_range(n_q, _sharded)  # queries are independent: each rank classifies its slice
-        g = tuple(to_device_f64(a[lo:hi]) for a in global_xyz)
+        mine = _query_slice(n_q, _sharded)  # queries are independent: each rank classifies its share
+        g = tuple(to_device_f64(a[mine]) for a in global_xyz)
         lam = tuple(to_device_f64(a) for a in lam_xyz)
         idx, dist, _ = lam_index.query(g, k=neighbours)
-        out = torch.empty((hi - lo,), dtype=torch.uint8, device=idx.device)
+        n_mine = int(g[0].shape[0])
+        out = torch.empty((n_mine,), dtype=torch.uint8, device=idx.device)
         max_distance = -1.0 if max_distance_km is None else max_distance_km / R_earth_km
         call(
             "at_cutout_classify",
             _ptr(lam[0]), _ptr(lam[1]), _ptr(lam[2]), n_lam,
-            _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), hi - lo,
+            _ptr(g[0]), _ptr(g[1]), _ptr(g[2]), n_mine,
             _ptr(idx), _ptr(dist), int(neighbours),
             float(min_distance), float(max_distance), int(CUTOUT_DOT_MODE),
             _ptr(out), stream_ptr(),
@@ -275,13 +311,23 @@ def thinning_mask(
     """Indices of the LAM points closest to each (cropped) global point (spatial.py:443-503)."""
     _check_latlon_arrays(lats, lons, global_lats, global_lons)
     require_cuda()
+    ph = _Phases("thinning_mask")
     mask = cropping_mask(global_lats, global_lons, *_crop_box(lats, lons, cropping_distance))
+    ph.mark("crop")
     global_xyz = _xyz(global_lats[mask], global_lons[mask], _sharded)
-    index = KnnIndex(_xyz(lats, lons, _sharded))
+    ph.mark("xyz global")
+    lam_xyz = _xyz(lats, lons, _sharded)
+    ph.mark("xyz lam")
+    index = KnnIndex(lam_xyz)
+    ph.mark("build")
     n_q = int(global_xyz[0].shape[0])
-    lo, hi = _query_range(n_q, _sharded)
-    idx, _, _ = index.query(tuple(a[lo:hi] for a in global_xyz), k=1)
-    return _gather_queries(idx[:, 0].contiguous(), n_q, _sharded).cpu().numpy()
+    mine = _query_slice(n_q, _sharded)
+    idx, _, _ = index.query(tuple(a[mine] for a in global_xyz), k=1)
+    ph.mark("query")
+    out = _gather_queries(idx[:, 0].contiguous(), n_q, _sharded).cpu().numpy()
+    ph.mark("gather + D2H")
+    ph.report()
+    return out
 
 
 def global_on_lam_mask(

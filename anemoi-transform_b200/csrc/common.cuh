@@ -44,6 +44,15 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 // Number of SMs of the current device (cached per device).
 int sm_count();
 
+// Device memory for the library's handles and temporaries, from a per-device cache of freed
+// blocks.  cudaMalloc / cudaFree cost milliseconds each once several processes share a box (the
+// driver maps and unmaps under a lock): the 15 buffers of one kNN index were 11 ms to allocate
+// on an idle box and 150 ms with four ranks doing the same.  device_free waits for the device
+// like cudaFree does (the block may still be in use by queued kernels) and keeps the block for
+// the next request of the same size; at_device_cache_trim() returns everything to the driver.
+cudaError_t device_alloc(void** p, size_t bytes);
+void device_free(void* p);
+
 constexpr int kWarp = 32;
 
 // Streaming (evict-first) 16-byte store: Y is written once and never re-read by the kernel.

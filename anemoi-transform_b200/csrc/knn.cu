@@ -729,10 +729,10 @@ using namespace at;
 namespace {
 
 int dev_alloc(at_knn* k, void** p, size_t bytes) {
-    cudaError_t e = cudaMalloc(p, bytes > 0 ? bytes : 16);
+    cudaError_t e = device_alloc(p, bytes > 0 ? bytes : 16);
     if (e != cudaSuccess)
         return set_error(e == cudaErrorMemoryAllocation ? AT_ERR_NOMEM : AT_ERR_CUDA,
-                         "at_knn_create: cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+                         "at_knn_create: device allocation (%zu) failed: %s", bytes, cudaGetErrorString(e));
     k->owned.push_back(*p);
     return AT_OK;
 }
@@ -748,7 +748,7 @@ double dec_ordered(unsigned long long u) {
 
 extern "C" int at_knn_destroy(at_knn_t* k) {
     if (k == nullptr) return AT_OK;
-    for (void* p : k->owned) cudaFree(p);
+    for (void* p : k->owned) device_free(p);
     delete k;
     return AT_OK;
 }
@@ -1004,13 +1004,55 @@ __global__ void peer_signal_wait_kernel(const PeerFlags f, unsigned long long ep
     }
 }
 
+// The exchange as one coalesced pass after the search: every thread copies 16-byte pieces of
+// this rank's slice into every peer's gather buffer (long contiguous NVLink writes instead of
+// one 8-byte store per query and peer from inside the search, which at 8 GPUs tripled the
+// search kernel's time); the last CTA to finish then runs the arrival-flag exchange.
+__global__ void __launch_bounds__(256)
+    peer_broadcast_kernel(const PeerOut peers, const long long* __restrict__ mine, long long n_items,
+                          const PeerFlags f, unsigned long long epoch, unsigned int* __restrict__ done_ctas,
+                          int* __restrict__ error) {
+    const long long n2 = n_items / 2;  // int64 pairs (the slice starts 16-byte aligned)
+    const longlong2* src = reinterpret_cast<const longlong2*>(mine);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+        const longlong2 v = src[i];
+        for (int p = 0; p < peers.n; ++p) reinterpret_cast<longlong2*>(peers.ptr[p])[i] = v;
+    }
+    if ((n_items & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+        for (int p = 0; p < peers.n; ++p) peers.ptr[p][n_items - 1] = mine[n_items - 1];
+    __threadfence_system();
+    __shared__ bool last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = atomicAdd(done_ctas, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!last) return;
+    if (threadIdx.x == 0) *done_ctas = 0;  // ready for the next call on this stream
+    const int r = threadIdx.x;
+    if (r >= f.world) return;
+    __threadfence_system();
+    unsigned long long* theirs = f.ptr[r] + f.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+    const unsigned long long* own = f.ptr[f.rank] + r;
+    unsigned long long t0, now, seen;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(own) : "memory");
+        if (seen >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > 2000000000ull) {
+            *error = 1;
+            break;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int at_knn_query_gather(const at_knn_t* k, const double* qx, const double* qy, const double* qz,
                                    int64_t nq_local, int kk, double upper_bound, int64_t* const* gather_bufs,
                                    uint64_t* const* flag_bufs, int world, int rank, int64_t row_offset,
                                    double* dist_out, uint8_t* tie_out, uint64_t epoch, int32_t* error_flag,
-                                   void* stream) {
+                                   int exchange, void* stream) {
     AT_REQUIRE(k != nullptr && gather_bufs != nullptr && flag_bufs != nullptr && error_flag != nullptr,
                "at_knn_query_gather: null argument");
     AT_REQUIRE(world >= 1 && world <= kMaxPeers + 1 && rank >= 0 && rank < world, "at_knn_query_gather: bad rank %d of %d",
@@ -1020,15 +1062,17 @@ extern "C" int at_knn_query_gather(const at_knn_t* k, const double* qx, const do
     AT_REQUIRE(!(upper_bound != upper_bound) && upper_bound >= 0, "at_knn_query_gather: bad distance_upper_bound");
     for (int r = 0; r < world; ++r)
         AT_REQUIRE(gather_bufs[r] != nullptr && flag_bufs[r] != nullptr, "at_knn_query_gather: rank %d has no buffer", r);
+    AT_REQUIRE(exchange == AT_EXCHANGE_INLINE || exchange == AT_EXCHANGE_BULK, "at_knn_query_gather: unknown exchange mode %d", exchange);
     cudaStream_t st = as_stream(stream);
+    PeerOut peers, none;
+    peers.n = none.n = 0;
+    for (int r = 0; r < world; ++r)
+        if (r != rank) peers.ptr[peers.n++] = reinterpret_cast<long long*>(gather_bufs[r]) + row_offset * kk;
+    long long* mine = reinterpret_cast<long long*>(gather_bufs[rank]) + row_offset * kk;
+    const bool bulk = exchange == AT_EXCHANGE_BULK && world > 1 && (reinterpret_cast<uintptr_t>(mine) & 15) == 0;
     if (nq_local > 0) {
         AT_REQUIRE(qx != nullptr && qy != nullptr && qz != nullptr, "at_knn_query_gather: null queries");
-        PeerOut peers;
-        peers.n = 0;
-        for (int r = 0; r < world; ++r)
-            if (r != rank) peers.ptr[peers.n++] = reinterpret_cast<long long*>(gather_bufs[r]) + row_offset * kk;
-        int rc = launch_knn_query(k, qx, qy, qz, nq_local, kk, upper_bound,
-                                  reinterpret_cast<long long*>(gather_bufs[rank]) + row_offset * kk, dist_out, tie_out, peers, st);
+        int rc = launch_knn_query(k, qx, qy, qz, nq_local, kk, upper_bound, mine, dist_out, tie_out, bulk ? none : peers, st);
         if (rc != AT_OK) return rc;
     }
     if (world > 1) {
@@ -1036,8 +1080,17 @@ extern "C" int at_knn_query_gather(const at_knn_t* k, const double* qx, const do
         f.world = world;
         f.rank = rank;
         for (int r = 0; r < world; ++r) f.ptr[r] = reinterpret_cast<unsigned long long*>(flag_bufs[r]);
-        peer_signal_wait_kernel<<<1, 32, 0, st>>>(f, epoch, error_flag);
-        AT_LAUNCH_CHECK("peer_signal_wait_kernel");
+        if (bulk) {
+            // the CTA counter lives behind the flags of this rank's own buffer (uint64[world] flags, then the counter)
+            unsigned int* counter = reinterpret_cast<unsigned int*>(f.ptr[rank] + world);
+            const long long n_items = nq_local * kk;
+            const unsigned blocks = static_cast<unsigned>(std::max<long long>(1, std::min<long long>((n_items / 2 + 255) / 256, 4ll * sm_count())));
+            peer_broadcast_kernel<<<blocks, 256, 0, st>>>(peers, mine, n_items, f, epoch, counter, error_flag);
+            AT_LAUNCH_CHECK("peer_broadcast_kernel");
+        } else {
+            peer_signal_wait_kernel<<<1, 32, 0, st>>>(f, epoch, error_flag);
+            AT_LAUNCH_CHECK("peer_signal_wait_kernel");
+        }
     }
     return AT_OK;
 }
@@ -1117,7 +1170,7 @@ extern "C" int at_min_nn_distance(const at_knn_t* k, int64_t first, int64_t coun
         return AT_OK;
     }
     unsigned long long* d_bits = nullptr;
-    AT_CUDA_TRY(cudaMalloc(&d_bits, 8));
+    AT_CUDA_TRY(device_alloc(reinterpret_cast<void**>(&d_bits), 8));
     const double inf = INFINITY;
     unsigned long long init;
     memcpy(&init, &inf, 8);
@@ -1130,7 +1183,7 @@ extern "C" int at_min_nn_distance(const at_knn_t* k, int64_t first, int64_t coun
     unsigned long long bits = init;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&bits, d_bits, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_bits);
+    device_free(d_bits);
     if (e != cudaSuccess) return set_error(AT_ERR_CUDA, "at_min_nn_distance: %s", cudaGetErrorString(e));
     memcpy(out_host, &bits, 8);
     return AT_OK;

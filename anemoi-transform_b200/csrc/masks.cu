@@ -273,10 +273,10 @@ extern "C" int at_compact_mask(const uint8_t* mark, int64_t n, int64_t* out_idx,
     AT_REQUIRE(blocks < (1ll << 31), "at_compact_mask: too large");
     int32_t* d_counts = nullptr;
     long long* d_offsets = nullptr;
-    AT_CUDA_TRY(cudaMalloc(&d_counts, static_cast<size_t>(blocks) * 4));
-    cudaError_t e = cudaMalloc(&d_offsets, (static_cast<size_t>(blocks) + 1) * 8);
+    AT_CUDA_TRY(device_alloc(reinterpret_cast<void**>(&d_counts), static_cast<size_t>(blocks) * 4));
+    cudaError_t e = device_alloc(reinterpret_cast<void**>(&d_offsets), (static_cast<size_t>(blocks) + 1) * 8);
     if (e != cudaSuccess) {
-        cudaFree(d_counts);
+        device_free(d_counts);
         return set_error(AT_ERR_NOMEM, "at_compact_mask: %s", cudaGetErrorString(e));
     }
     compact_count_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(mark, n, d_counts);
@@ -287,8 +287,8 @@ extern "C" int at_compact_mask(const uint8_t* mark, int64_t n, int64_t* out_idx,
     long long total = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_offsets + blocks, 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-    cudaFree(d_counts);
-    cudaFree(d_offsets);
+    device_free(d_counts);
+    device_free(d_offsets);
     if (e != cudaSuccess) return set_error(AT_ERR_CUDA, "at_compact_mask: %s", cudaGetErrorString(e));
     *count_host = total;
     return AT_OK;

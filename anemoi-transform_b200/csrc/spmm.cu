@@ -671,6 +671,26 @@ static int launch_f32(const at_csr* csr, const SpmmArgs& args, bool bulk, bool f
     return AT_OK;
 }
 
+// first[c] / last[c] = first / last row whose segment references column c (live-column span)
+__global__ void col_span_kernel(const int* __restrict__ indptr, const int* __restrict__ indices, int n_rows,
+                                int* __restrict__ first, int* __restrict__ last) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    for (int p = indptr[r]; p < indptr[r + 1]; ++p) {
+        const int col = indices[p];
+        atomicMin(first + col, r);
+        atomicMax(last + col, r);
+    }
+}
+__global__ void col_span_sum_kernel(const int* __restrict__ first, const int* __restrict__ last, long long n_cols,
+                                    unsigned long long* __restrict__ sum) {
+    unsigned long long local = 0;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n_cols; c += (long long)gridDim.x * blockDim.x)
+        if (last[c] >= 0) local += static_cast<unsigned long long>(last[c] - first[c] + 1);
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(sum, local);
+}
+
 template <typename T>
 static bool copy_index_array(const void* src, int dtype, int64_t n, std::vector<int32_t>& dst,
                              int64_t limit, const char* what, bool monotone) {
@@ -739,24 +759,6 @@ extern "C" int at_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const 
         const int64_t e = std::min<int64_t>(n_rows, r + kMaxRowsPerCta);
         c->max_seg64 = std::max(c->max_seg64, h_ptr[static_cast<size_t>(e)] - h_ptr[static_cast<size_t>(r)]);
     }
-    {
-        // Reuse working set: a source column is "live" between the first and the last target
-        // row that references it; the mean number of live columns while the rows are walked in
-        // order is sum(span) / n_rows.  at_spmm sizes its column super-tile so that the live
-        // source rows of the CTAs in flight stay in L2.
-        std::vector<int32_t> first(static_cast<size_t>(n_cols), -1), last(static_cast<size_t>(n_cols), -1);
-        for (int64_t r = 0; r < n_rows; ++r)
-            for (int32_t p = h_ptr[static_cast<size_t>(r)]; p < h_ptr[static_cast<size_t>(r + 1)]; ++p) {
-                const size_t col = static_cast<size_t>(h_idx[static_cast<size_t>(p)]);
-                if (first[col] < 0) first[col] = static_cast<int32_t>(r);
-                last[col] = static_cast<int32_t>(r);
-            }
-        double span = 0;
-        for (int64_t col = 0; col < n_cols; ++col)
-            if (first[static_cast<size_t>(col)] >= 0)
-                span += static_cast<double>(last[static_cast<size_t>(col)] - first[static_cast<size_t>(col)] + 1);
-        c->live_cols = n_rows > 0 ? span / static_cast<double>(n_rows) : 0.0;
-    }
     cudaGetDevice(&c->device);
 
     const size_t esz = data_dtype == AT_F32 ? 4 : 8;
@@ -765,9 +767,9 @@ extern "C" int at_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const 
         return code;
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&c->d_indptr, (static_cast<size_t>(n_rows) + 1 + kPad) * 4)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_indices, (static_cast<size_t>(nnz) + kPad) * 4)) != cudaSuccess ||
-        (e = cudaMalloc(&c->d_data, (static_cast<size_t>(nnz) + kPad) * esz)) != cudaSuccess) {
+    if ((e = device_alloc(reinterpret_cast<void**>(&c->d_indptr), (static_cast<size_t>(n_rows) + 1 + kPad) * 4)) != cudaSuccess ||
+        (e = device_alloc(reinterpret_cast<void**>(&c->d_indices), (static_cast<size_t>(nnz) + kPad) * 4)) != cudaSuccess ||
+        (e = device_alloc(reinterpret_cast<void**>(&c->d_data), (static_cast<size_t>(nnz) + kPad) * esz)) != cudaSuccess) {
         set_error(e == cudaErrorMemoryAllocation ? AT_ERR_NOMEM : AT_ERR_CUDA,
                   "at_csr_create: cudaMalloc failed: %s", cudaGetErrorString(e));
         return fail(e == cudaErrorMemoryAllocation ? AT_ERR_NOMEM : AT_ERR_CUDA);
@@ -784,15 +786,46 @@ extern "C" int at_csr_create(int64_t n_rows, int64_t n_cols, int64_t nnz, const 
         set_error(AT_ERR_CUDA, "at_csr_create: staging the matrix failed: %s", cudaGetErrorString(e));
         return fail(AT_ERR_CUDA);
     }
+    {
+        // Reuse working set: a source column is "live" between the first and the last target
+        // row that references it; the mean number of live columns while the rows are walked in
+        // order is sum(span) / n_rows.  at_spmm sizes its column super-tile so that the live
+        // source rows of the CTAs in flight stay in L2.  Computed on the device from the staged
+        // arrays (the scattered first / last updates were the slowest part of the host set-up
+        // for matrices with millions of nonzeros).
+        int32_t *d_first = nullptr, *d_last = nullptr;
+        unsigned long long* d_sum = nullptr;
+        c->live_cols = 0.0;
+        if (n_rows > 0 && n_cols > 0 && nnz > 0) {
+            const size_t cb = static_cast<size_t>(n_cols) * 4;
+            unsigned long long h_sum = 0;
+            if ((e = device_alloc(reinterpret_cast<void**>(&d_first), cb)) == cudaSuccess && (e = device_alloc(reinterpret_cast<void**>(&d_last), cb)) == cudaSuccess &&
+                (e = device_alloc(reinterpret_cast<void**>(&d_sum), 8)) == cudaSuccess && (e = cudaMemset(d_first, 0x7f, cb)) == cudaSuccess &&
+                (e = cudaMemset(d_last, 0xff, cb)) == cudaSuccess && (e = cudaMemset(d_sum, 0, 8)) == cudaSuccess) {
+                col_span_kernel<<<static_cast<unsigned>((n_rows + 255) / 256), 256>>>(c->d_indptr, c->d_indices, static_cast<int>(n_rows), d_first, d_last);
+                col_span_sum_kernel<<<static_cast<unsigned>(std::min<int64_t>((n_cols + 255) / 256, 1024)), 256>>>(d_first, d_last, n_cols, d_sum);
+                e = cudaGetLastError();
+                if (e == cudaSuccess) e = cudaMemcpy(&h_sum, d_sum, 8, cudaMemcpyDeviceToHost);
+            }
+            device_free(d_first);
+            device_free(d_last);
+            device_free(d_sum);
+            if (e != cudaSuccess) {
+                set_error(AT_ERR_CUDA, "at_csr_create: column-span scan failed: %s", cudaGetErrorString(e));
+                return fail(AT_ERR_CUDA);
+            }
+            c->live_cols = static_cast<double>(h_sum) / static_cast<double>(n_rows);
+        }
+    }
     *out = c;
     return AT_OK;
 }
 
 extern "C" int at_csr_destroy(at_csr_t* c) {
     if (c == nullptr) return AT_OK;
-    cudaFree(c->d_indptr);
-    cudaFree(c->d_indices);
-    cudaFree(c->d_data);
+    device_free(c->d_indptr);
+    device_free(c->d_indices);
+    device_free(c->d_data);
     delete c;
     return AT_OK;
 }
@@ -960,9 +993,9 @@ extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_se
     e->n_out_cols = n_out_cols;
     cudaGetDevice(&e->device);
     cudaError_t ce;
-    if ((ce = cudaMalloc(&e->d_tiles, tiles.size() * sizeof(EpiTile))) != cudaSuccess ||
-        (ce = cudaMalloc(&e->d_cols32, h32.size() * sizeof(ColF32))) != cudaSuccess ||
-        (ce = cudaMalloc(&e->d_cols64, h64.size() * sizeof(ColF64))) != cudaSuccess ||
+    if ((ce = device_alloc(reinterpret_cast<void**>(&e->d_tiles), tiles.size() * sizeof(EpiTile))) != cudaSuccess ||
+        (ce = device_alloc(reinterpret_cast<void**>(&e->d_cols32), h32.size() * sizeof(ColF32))) != cudaSuccess ||
+        (ce = device_alloc(reinterpret_cast<void**>(&e->d_cols64), h64.size() * sizeof(ColF64))) != cudaSuccess ||
         (ce = cudaMemcpy(e->d_tiles, tiles.data(), tiles.size() * sizeof(EpiTile), cudaMemcpyHostToDevice)) !=
             cudaSuccess ||
         (ce = cudaMemcpy(e->d_cols32, h32.data(), h32.size() * sizeof(ColF32), cudaMemcpyHostToDevice)) !=
@@ -978,9 +1011,9 @@ extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_se
 
 extern "C" int at_epilogue_destroy(at_epilogue_t* e) {
     if (e == nullptr) return AT_OK;
-    cudaFree(e->d_tiles);
-    cudaFree(e->d_cols32);
-    cudaFree(e->d_cols64);
+    device_free(e->d_tiles);
+    device_free(e->d_cols32);
+    device_free(e->d_cols64);
     delete e;
     return AT_OK;
 }

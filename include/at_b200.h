@@ -60,6 +60,10 @@ AT_API int at_version(void);
 AT_API int at_device_count(int* count);
 AT_API int at_set_device(int device);
 /* Pin / unpin an existing host allocation so the async copies of at_pipeline_* overlap. */
+/* Return the library's cached device blocks (handles and temporaries recycle their memory
+ * instead of calling cudaMalloc / cudaFree every time; AT_B200_DEVICE_CACHE_MB caps the cache,
+ * default 4096) to the driver. */
+AT_API int at_device_cache_trim(void);
 AT_API int at_host_register(void* ptr, size_t bytes);
 AT_API int at_host_unregister(void* ptr);
 
@@ -364,12 +368,18 @@ AT_API int at_knn_query(const at_knn_t* knn, const double* qx, const double* qy,
  * `epoch` increases by one per call on every rank.  A rank that does not arrive within 2 s
  * sets *error_flag (device int32) instead of hanging.  dist_out / tie_out are local
  * ([nq_local, k] / [nq_local]) or NULL.  world <= 16.
+ * exchange: AT_EXCHANGE_INLINE — the search kernels store to the peers as they finish each
+ * query; AT_EXCHANGE_BULK — the search writes this rank's slice only and one kernel after it
+ * copies the slice to every peer with coalesced 16-byte stores, its last CTA running the flag
+ * exchange (flag_bufs[r] must then be uint64[world + 1]: the CTA counter follows the flags).
  */
+#define AT_EXCHANGE_INLINE 0
+#define AT_EXCHANGE_BULK 1
 AT_API int at_knn_query_gather(const at_knn_t* knn, const double* qx, const double* qy, const double* qz,
                         int64_t nq_local, int k, double upper_bound,
                         int64_t* const* gather_bufs, uint64_t* const* flag_bufs, int world, int rank,
                         int64_t row_offset, double* dist_out, uint8_t* tie_out, uint64_t epoch,
-                        int32_t* error_flag, void* stream);
+                        int32_t* error_flag, int exchange, void* stream);
 /* Device memory that the other processes of the box can map: zero-filled, `handle` receives the
  * 64-byte inter-process handle to send to the peers; at_peer_open maps a peer's buffer. */
 AT_API int at_peer_alloc(size_t bytes, void** ptr, void* handle);

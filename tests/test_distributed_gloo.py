@@ -64,11 +64,15 @@ def _worker(rank: int, ws: int, port: int, out_dir: str):
         # fewer queries than ranks: the trailing rank owns an empty range and must still take part
         # in the collective (it used to raise before the all-gather and hang the others)
         one = atd.sharded_query(1, lambda lo, hi: torch.from_numpy(np.asarray(tree.query(tgt[lo:hi], k=3)[1]).reshape(hi - lo, 3)))
+        # interleaved split (rank::ws) and its inverse
+        full = torch.arange(23 * 2, dtype=torch.int64).reshape(23, 2)
+        inter = atd.all_gather_strided(full[rank::ws].contiguous(), 23)
+        inter1 = atd.all_gather_strided(torch.arange(7)[rank::ws].contiguous(), 7)
         # host trigonometry sharded over the ranks, slices all-gathered: bitwise the single-process xyz
         atd.LATLON_SHARD_MIN_POINTS = 0
         lat, lon = syn.octahedral(13)
         xyz = atd.latlon_to_xyz_device(lat, lon, _device="cpu")
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.numpy(), mark=mark.numpy(), res=res, mine=np.array(mine), one=one.numpy(), xyz=np.stack([t.numpy() for t in xyz]))
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), idx=idx.numpy(), mark=mark.numpy(), res=res, mine=np.array(mine), one=one.numpy(), xyz=np.stack([t.numpy() for t in xyz]), inter=inter.numpy(), inter1=inter1.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -96,6 +100,7 @@ def test_world_size_2_gloo(tmp_path):
         assert np.array_equal(o["mark"], want_mark) and want_mark.sum() > 0
         assert float(o["res"]) == want_res
         assert np.array_equal(o["one"], want_idx[:1])
+        assert np.array_equal(o["inter"], np.arange(46).reshape(23, 2)) and np.array_equal(o["inter1"], np.arange(7))
         assert np.array_equal(o["xyz"].view(np.uint64), np.array(osp.latlon_to_xyz(*syn.octahedral(13))).view(np.uint64))
     assert sorted(np.concatenate([o["mine"] for o in outs]).tolist()) == list(range(22))
     assert outs[0]["mine"].tolist() == list(range(12))  # 22 fields, multiples of 4 → 12 + 10
