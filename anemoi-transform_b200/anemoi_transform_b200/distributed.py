@@ -193,7 +193,7 @@ class ShardedKnnQuery:
     peer mapping is unavailable the queries write straight into this rank's slice of a
     preallocated buffer and NCCL all-gathers it in place (no per-step allocation either)."""
 
-    def __init__(self, index, qxyz, k: int = 1, distance_upper_bound: float = float("inf"), mode: str = "auto", exchange: str = "bulk"):
+    def __init__(self, index, qxyz, k: int = 1, distance_upper_bound: float = float("inf"), mode: str = "auto", exchange: str = "bulk", graph: bool = True):
         import torch
 
         from .device import to_device_f64
@@ -210,6 +210,7 @@ class ShardedKnnQuery:
         self.epoch = 0
         self.peers = None
         self.exchange = exchange
+        self._use_graph, self._graphs = bool(graph), None
         rows = max(1, self.world * self.per)
         self.mode = "local" if self.world == 1 else mode
         if self.mode in ("auto", "peer"):
@@ -246,9 +247,32 @@ class ShardedKnnQuery:
         if self.mode == "peer":
             self.epoch += 1
             slot = self.epoch & 1
-            call("at_knn_query_gather", self.index._h, _ptr(self.q[0]), _ptr(self.q[1]), _ptr(self.q[2]), n_local, self.k, self.ub,
-                 self._gather[slot], self._flags, self.world, self.rank, self.lo, None, None, self.epoch, _ptr(self._error),
-                 EXCHANGE_BULK if self.exchange == "bulk" else EXCHANGE_INLINE, stream_ptr())  # fmt: skip
+
+            def launch():  # epoch 0: the library counts the calls on the device (replayable)
+                call("at_knn_query_gather", self.index._h, _ptr(self.q[0]), _ptr(self.q[1]), _ptr(self.q[2]), n_local, self.k, self.ub,
+                     self._gather[slot], self._flags, self.world, self.rank, self.lo, None, None, 0, _ptr(self._error),
+                     EXCHANGE_BULK if self.exchange == "bulk" else EXCHANGE_INLINE, stream_ptr())  # fmt: skip
+
+            if not self._use_graph:
+                launch()
+            else:
+                # A step is three short kernels; at 8 GPUs the host spends longer launching them
+                # than the GPU running them.  Each slot's step is captured once (the first two
+                # calls run eagerly and warm everything up) and replayed with one graph launch.
+                import torch
+
+                if self._graphs is None:
+                    self._graphs = {}
+                if self.epoch <= 2:
+                    launch()
+                elif slot not in self._graphs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        launch()
+                    self._graphs[slot] = g
+                    g.replay()
+                else:
+                    self._graphs[slot].replay()
             return self._views[slot][: self.nq]
         mine = self._out[self.lo : self.lo + n_local]
         if n_local:
@@ -279,6 +303,7 @@ class ShardedKnnQuery:
         }[self.mode]
 
     def close(self) -> None:
+        self._graphs = None
         if self.peers is not None:
             self._views = []
             self.peers.close()

@@ -984,7 +984,19 @@ struct PeerFlags {
 // Thread r tells rank r "rank `rank` has finished epoch `epoch`" (release: the peer stores of the
 // kernels before this one on the stream are visible first), then waits until rank r has said the
 // same to us.  A rank that never arrives trips the timeout instead of hanging the GPU.
-__global__ void peer_signal_wait_kernel(const PeerFlags f, unsigned long long epoch, int* __restrict__ error) {
+// `epoch` = 0: the epoch is this rank's own call counter, kept in device memory behind its flags
+// (every rank makes the same sequence of calls), so the launch has no per-call arguments and a
+// whole step can be replayed as a CUDA graph.
+__device__ __forceinline__ unsigned long long next_epoch(unsigned long long epoch, unsigned long long* counter) {
+    __shared__ unsigned long long shared_epoch;
+    if (threadIdx.x == 0) shared_epoch = epoch != 0 ? epoch : ++(*counter);
+    __syncthreads();
+    return shared_epoch;
+}
+
+__global__ void peer_signal_wait_kernel(const PeerFlags f, unsigned long long epoch_arg, unsigned long long* __restrict__ counter,
+                                        int* __restrict__ error) {
+    const unsigned long long epoch = next_epoch(epoch_arg, counter);
     const int r = threadIdx.x;
     if (r >= f.world) return;
     __threadfence_system();
@@ -1010,8 +1022,8 @@ __global__ void peer_signal_wait_kernel(const PeerFlags f, unsigned long long ep
 // search kernel's time); the last CTA to finish then runs the arrival-flag exchange.
 __global__ void __launch_bounds__(256)
     peer_broadcast_kernel(const PeerOut peers, const long long* __restrict__ mine, long long n_items,
-                          const PeerFlags f, unsigned long long epoch, unsigned int* __restrict__ done_ctas,
-                          int* __restrict__ error) {
+                          const PeerFlags f, unsigned long long epoch_arg, unsigned long long* __restrict__ counter,
+                          unsigned int* __restrict__ done_ctas, int* __restrict__ error) {
     const long long n2 = n_items / 2;  // int64 pairs (the slice starts 16-byte aligned)
     const longlong2* src = reinterpret_cast<const longlong2*>(mine);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
@@ -1027,6 +1039,7 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     if (!last) return;
     if (threadIdx.x == 0) *done_ctas = 0;  // ready for the next call on this stream
+    const unsigned long long epoch = next_epoch(epoch_arg, counter);
     const int r = threadIdx.x;
     if (r >= f.world) return;
     __threadfence_system();
@@ -1080,15 +1093,17 @@ extern "C" int at_knn_query_gather(const at_knn_t* k, const double* qx, const do
         f.world = world;
         f.rank = rank;
         for (int r = 0; r < world; ++r) f.ptr[r] = reinterpret_cast<unsigned long long*>(flag_bufs[r]);
+        // behind the uint64[world] flags of this rank's own buffer: the CTA counter of the bulk
+        // exchange, then the call counter that serves as the epoch when the caller passes 0
+        unsigned long long* epoch_counter = f.ptr[rank] + world + 1;
         if (bulk) {
-            // the CTA counter lives behind the flags of this rank's own buffer (uint64[world] flags, then the counter)
             unsigned int* counter = reinterpret_cast<unsigned int*>(f.ptr[rank] + world);
             const long long n_items = nq_local * kk;
             const unsigned blocks = static_cast<unsigned>(std::max<long long>(1, std::min<long long>((n_items / 2 + 255) / 256, 4ll * sm_count())));
-            peer_broadcast_kernel<<<blocks, 256, 0, st>>>(peers, mine, n_items, f, epoch, counter, error_flag);
+            peer_broadcast_kernel<<<blocks, 256, 0, st>>>(peers, mine, n_items, f, epoch, epoch_counter, counter, error_flag);
             AT_LAUNCH_CHECK("peer_broadcast_kernel");
         } else {
-            peer_signal_wait_kernel<<<1, 32, 0, st>>>(f, epoch, error_flag);
+            peer_signal_wait_kernel<<<1, 32, 0, st>>>(f, epoch, epoch_counter, error_flag);
             AT_LAUNCH_CHECK("peer_signal_wait_kernel");
         }
     }

@@ -365,7 +365,10 @@ AT_API int at_knn_query(const at_knn_t* knn, const double* qx, const double* qy,
  * gather_bufs[rank].  Replaces query + ncclAllGather (spatial.py:628-632 run by
  * N ranks).  gather_bufs / flag_bufs: HOST arrays of `world` device pointers (own buffers from
  * at_peer_alloc, the others' from at_peer_open); flag_bufs[r] is uint64[world], zero at start;
- * `epoch` increases by one per call on every rank.  A rank that does not arrive within 2 s
+ * `epoch` increases by one per call on every rank — or is 0, and the library counts the calls
+ * itself in device memory (flag_bufs[r] is then uint64[world + 2]), which leaves the launch
+ * without per-call arguments so that a step can be captured once and replayed as a CUDA graph.
+ * A rank that does not arrive within 2 s
  * sets *error_flag (device int32) instead of hanging.  dist_out / tie_out are local
  * ([nq_local, k] / [nq_local]) or NULL.  world <= 16.
  * exchange: AT_EXCHANGE_INLINE — the search kernels store to the peers as they finish each
