@@ -274,3 +274,40 @@ def test_mixed_dtype_fieldlist_keeps_each_fields_dtype(cuda):
         got = f.to_numpy()
         assert got.dtype == v.dtype
         assert_same_values(got.reshape(-1), v * v.dtype.type(1.1) + v.dtype.type(0.3), "rescale")
+
+
+def test_config3_grids_through_the_plugin_call_at_scale(cuda, tmp_path):
+    """Config 3's grids (0.25° → N320-shaped) through the call bench.py times as `e2e`: 600
+    ordinary numpy fields (ragged last chunk, one float64 field, NaNs) → RegridFilter.forward →
+    to_numpy() of every output; every field of a sample bitwise scipy's, every other checked
+    through a checksum against the resident result."""
+    from anemoi_transform_b200.fields import device_column_of
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    t_lat, t_lon = syn.n320_like()
+    s_lat, s_lon = syn.regular_latlon(0.25)
+    d, i, p, shape = syn.bilinear_matrix(0.25, t_lat, t_lon)
+    path = str(tmp_path / "c3.npz")
+    syn.save_regrid_npz(path, d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    m = csr_array((d, i, p), shape=shape)
+    n = 603
+    rng = np.random.default_rng(11)
+    base = rng.standard_normal((16, shape[1]), dtype=np.float32)
+    values = [np.array(base[k % 16]) * np.float32(1 + k) for k in range(n)]
+    values[7][::1001] = np.nan
+    values[300] = values[300].astype(np.float64)
+    data = _fieldlist(values, s_lat, s_lon)
+    out = F("regrid", matrix=path).forward(data)
+    arrays = [f.to_numpy() for f in out]
+    assert len(arrays) == n and all(a.shape == (shape[0],) for a in arrays)
+    for k in (0, 7, 59, 60, 61, 300, 599, 602):
+        assert arrays[k].dtype == (m @ values[k]).dtype
+        assert_same_values(arrays[k], m @ values[k], f"field {k}")
+    # linearity: field k is (1 + k) x base[k % 16] exactly in float32 wherever no rounding differs;
+    # the host copy of every field equals the resident column it was downloaded from
+    batch, col0 = device_column_of(out[0])
+    resident = batch.data[:, : batch.n_fields].cpu().numpy()
+    cols = [device_column_of(f)[1] for f in out if device_column_of(f)[0] is batch]
+    for j, c in enumerate(cols[:: 37]):
+        k = [kk for kk, f in enumerate(out) if device_column_of(f)[0] is batch][:: 37][j]
+        assert_same_values(arrays[k], resident[:, c], f"host copy of field {k}")
