@@ -38,7 +38,17 @@ struct KnnLevel {
     int shift;             // cell coordinate shift (level index); < 0 for the brute-force level
     double cover2;         // (kRingSafety · h_l)²: every source closer than this was scanned
     double h;              // cell edge h0 · 2^l
+    double inv_h;          // scale of the integer cell coordinates before `shift` (1/h0, or 1/h of a fine level)
+    int slot_ordered;      // sx/sy/sz follow this level's slots (level 0 only)
 };
+
+// Fine levels: cell edges h0/2, h0/4, … built only when some level-0 cell is crowded (a regular
+// lat-lon grid packs 1440 points into every ring around the poles, and 1440 copies of the pole
+// itself).  They are not part of the octree the far search walks; a query whose level-0 ring is
+// crowded starts at the fine level where that ring shrinks to ≈ 100 candidates.
+constexpr int kMaxFine = 4;
+constexpr int kDenseRing = 256;    // level-0 ring sizes above this try the fine levels first
+constexpr int kDenseTarget = 128;  // candidates a fine ring should hold
 
 struct KnnDev {
     const double *x, *y, *z;     // sources, original order
@@ -47,8 +57,13 @@ struct KnnDev {
     double ox, oy, oz;  // grid origin
     double inv_h0;
     int n_levels;       // including the brute-force level
+    int n_fine;         // fine levels below level 0 (0 for evenly spaced sources)
     KnnLevel lv[kMaxLevels];
+    KnnLevel fine[kMaxFine];  // fine[j]: cell edge h0 / 2^(j+1)
 };
+
+// Level by signed index: v >= 0 is lv[v], v < 0 is fine[-1 - v].
+__device__ __forceinline__ const KnnLevel& level_at(const KnnDev& d, int v) { return v < 0 ? d.fine[-1 - v] : d.lv[v]; }
 
 __device__ __forceinline__ uint32_t cell_hash(int cx, int cy, int cz) {
     uint32_t h = static_cast<uint32_t>(cx) * 73856093u ^ static_cast<uint32_t>(cy) * 19349663u ^
@@ -62,9 +77,10 @@ __device__ __forceinline__ uint32_t cell_hash(int cx, int cy, int cz) {
 }
 
 __device__ __forceinline__ int cell_coord(double p, double origin, double inv_h) {
-    double t = floor(__dmul_rn(__dsub_rn(p, origin), inv_h));
-    t = fmin(fmax(t, -1073741824.0), 1073741823.0);
-    return static_cast<int>(t);
+    // floor + clamp to [-2^30, 2^30): the conversion rounds towards -inf and saturates, the
+    // clamp is two integer instructions (fmin / fmax on doubles were 6 % of the query kernel)
+    const int c = __double2int_rd(__dmul_rn(__dsub_rn(p, origin), inv_h));
+    return min(max(c, -1073741824), 1073741823);
 }
 
 __device__ __forceinline__ double dist2(double qx, double qy, double qz, double px, double py, double pz) {
@@ -148,6 +164,15 @@ __global__ void bucket_count_kernel(const double* __restrict__ x, const double* 
     // one per point: the coarse levels of a 6.6 M-point build were serialised on 256 counters.
     const unsigned peers = __match_any_sync(0xffffffffu, b);
     if (live && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + b, __popc(peers));
+}
+
+// Largest bucket of a level (start[] is the exclusive scan, m + 1 entries).
+__global__ void max_bucket_kernel(const int32_t* __restrict__ start, uint32_t m, unsigned int* __restrict__ out) {
+    unsigned int c = 0;
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < m; b += gridDim.x * blockDim.x)
+        c = max(c, static_cast<unsigned int>(start[b + 1] - start[b]));
+    for (int o = 16; o > 0; o >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o));
+    if ((threadIdx.x & 31) == 0 && c) atomicMax(out, c);
 }
 
 __global__ void bucket_scatter_kernel(const int32_t* __restrict__ bucket_of, long long n,
@@ -269,6 +294,20 @@ __device__ __forceinline__ bool key_less(double d2a, long long ia, double d2b, l
     return d2a < d2b || (d2a == d2b && ia < ib);
 }
 
+// Warp-wide minimum of the keys (d², index) held one per lane, d² >= 0 or +inf, index < 2^31:
+// a non-negative double orders like its bit pattern, so three integer warp reductions (REDUX:
+// high word, low word among the lanes that hold the smallest high word, index among the lanes
+// that hold the smallest d²) replace five rounds of four shuffles and a 128-bit comparison.
+__device__ __forceinline__ void warp_min_key(double& d2, long long& idx) {
+    const unsigned hi = static_cast<unsigned>(__double2hiint(d2)), lo = static_cast<unsigned>(__double2loint(d2));
+    const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+    const bool holds = hi == mhi && lo == mlo;
+    const unsigned midx = __reduce_min_sync(0xffffffffu, holds ? static_cast<unsigned>(idx) : 0xffffffffu);
+    d2 = __hiloint2double(static_cast<int>(mhi), static_cast<int>(mlo));
+    idx = static_cast<long long>(midx);
+}
+
 // Flattened ring-1 candidate ranges of one query at one level, held across the warp:
 // lane j owns range [s0, s0 + cnt) at flat offset `off`; `total` candidates in all.
 struct Ring {
@@ -285,9 +324,9 @@ __device__ __forceinline__ Ring ring_ranges(const KnnDev& d, const KnnLevel& L, 
     } else {
         int b = -1 - lane;  // distinct dummy values for lanes >= 27
         if (lane < 27) {
-            const int cx = (cell_coord(qx, d.ox, d.inv_h0) >> L.shift) + (lane % 3) - 1;
-            const int cy = (cell_coord(qy, d.oy, d.inv_h0) >> L.shift) + ((lane / 3) % 3) - 1;
-            const int cz = (cell_coord(qz, d.oz, d.inv_h0) >> L.shift) + (lane / 9) - 1;
+            const int cx = (cell_coord(qx, d.ox, L.inv_h) >> L.shift) + (lane % 3) - 1;
+            const int cy = (cell_coord(qy, d.oy, L.inv_h) >> L.shift) + ((lane / 3) % 3) - 1;
+            const int cz = (cell_coord(qz, d.oz, L.inv_h) >> L.shift) + (lane / 9) - 1;
             b = static_cast<int>(cell_hash(cx, cy, cz) & L.mask);
         }
         const unsigned same = __match_any_sync(0xffffffffu, b);
@@ -371,14 +410,7 @@ __device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, 
             }
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, best.d2, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, best.idx, o);
-        if (key_less(od, oi, best.d2, best.idx)) {
-            best.d2 = od;
-            best.idx = oi;
-        }
-    }
+    warp_min_key(best.d2, best.idx);
     return best;
 }
 
@@ -427,14 +459,7 @@ __device__ __forceinline__ Cand select_cached(const KnnDev& d, const CandCache& 
             best.idx = idx;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        const double od = __shfl_xor_sync(0xffffffffu, best.d2, o);
-        const long long oi = __shfl_xor_sync(0xffffffffu, best.idx, o);
-        if (key_less(od, oi, best.d2, best.idx)) {
-            best.d2 = od;
-            best.idx = oi;
-        }
-    }
+    warp_min_key(best.d2, best.idx);
     return best;
 }
 
@@ -449,12 +474,25 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
                                             double& my_d2, long long& my_idx, const CandCache& cache) {
     unsigned tie = 0;
     done = true;
-    for (int level = 0; level < max_levels; ++level) {
-        const KnnLevel& L = d.lv[level];
+    // Crowded neighbourhood (warp-uniform: the ring total is the same in every lane): start at
+    // the fine level where the ring holds about kDenseTarget candidates and walk back up.
+    int first = 0;
+    Ring r0;
+    r0.s0 = r0.cnt = r0.off = r0.total = 0;
+    if (d.n_fine > 0 && max_levels > 0) {
+        r0 = ring_ranges(d, d.lv[0], qx, qy, qz, lane);
+        if (r0.total > kDenseRing) {
+            int halvings = 1;  // each halving of the cell edge divides a surface ring by about 4
+            while (halvings < d.n_fine && (r0.total >> (2 * halvings)) > kDenseTarget) ++halvings;
+            first = -halvings;
+        }
+    }
+    for (int level = first; level < max_levels; ++level) {
+        const KnnLevel& L = level_at(d, level);
         const bool last = level == d.n_levels - 1;
         // A level whose ring cannot decide anything (cover radius below the best possible
         // distance) is still scanned: cheap, and usually terminates at level 0.
-        const Ring r = ring_ranges(d, L, qx, qy, qz, lane);
+        const Ring r = (level == 0 && d.n_fine > 0) ? r0 : ring_ranges(d, L, qx, qy, qz, lane);
         my_d2 = INFINITY;
         my_idx = d.n;
         tie = 0;
@@ -463,10 +501,10 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         long long pidx = -1;
         int found = 0;
         const bool cached = CACHE && k > 1 && r.total <= kCandCap;  // warp-uniform
-        if (cached) fill_cache(d, L, level == 0, r, qx, qy, qz, ub2, lane, cache);
+        if (cached) fill_cache(d, L, L.slot_ordered != 0, r, qx, qy, qz, ub2, lane, cache);
         for (int j = 0; j < k; ++j) {
             const Cand c = cached ? select_cached(d, cache, r.total, pd2, pidx, lane)
-                                  : select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+                                  : select_next(d, L, L.slot_ordered != 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
             if (!(c.d2 < INFINITY)) break;
             if (j > 0 && c.d2 == pd2) tie |= 1u;
             if (lane == j) {
@@ -481,7 +519,7 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         if (complete || last || ub2 <= L.cover2) {
             if (want_tie && found == k) {
                 const Cand c = cached ? select_cached(d, cache, r.total, pd2, pidx, lane)
-                                      : select_next(d, L, level == 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+                                      : select_next(d, L, L.slot_ordered != 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
                 if (c.d2 == pd2) tie |= 2u;
             }
             __syncwarp();  // the cache is rewritten by the next level / query
@@ -506,7 +544,7 @@ struct PeerOut {
 
 // CACHE: k > 1, candidate keys cached in shared memory (knn_one); PEERS: also store to peers
 template <bool CACHE, bool PEERS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, CACHE ? 4 : 5)
     knn_query_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
                      const double* __restrict__ qz, long long nq, int k, double ub2, int near_levels,
                      long long* __restrict__ idx_out, double* __restrict__ dist_out,
@@ -520,7 +558,11 @@ __global__ void __launch_bounds__(256)
         cache.idx = reinterpret_cast<int*>(s_cache + (blockDim.x >> 5) * kCandCap * sizeof(double)) + warp * kCandCap;
     }
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
+    for (long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; w < nq; w += warps) {
+        // Grids run pole to pole, and a regular lat-lon source is crowded at both poles: the
+        // expensive queries sit at the two ends of the array.  Taking the queries from both ends
+        // inwards starts them first, so they overlap the cheap ones instead of forming the tail.
+        const long long q = (w & 1) ? nq - 1 - (w >> 1) : (w >> 1);
         const double x = qx[q], y = qy[q], z = qz[q];
         double d2;
         long long idx;
@@ -691,7 +733,7 @@ __global__ void __launch_bounds__(256)
                      uint8_t* __restrict__ mark) {
     const int lane = threadIdx.x & 31;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-    const KnnLevel& L = d.lv[level];
+    const KnnLevel& L = level_at(d, level);
     for (long long q = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; q < nq; q += warps) {
         const double x = qx[q], y = qy[q], z = qz[q];
         const Ring r = ring_ranges(d, L, x, y, z, lane);
@@ -701,7 +743,7 @@ __global__ void __launch_bounds__(256)
             if (t < r.total && s >= 0) {
                 double px, py, pz;
                 long long idx;
-                load_cand(d, L, level == 0, s, px, py, pz, idx);
+                load_cand(d, L, L.slot_ordered != 0, s, px, py, pz, idx);
                 if (dist2(x, y, z, px, py, pz) <= r2) mark[idx] = 1;
             }
         }
@@ -791,6 +833,8 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
     KNN_CUDA(cudaMemcpy(k->d_z, z, nb, kind));
 
     const unsigned pt_blocks = static_cast<unsigned>((n + 255) / 256);
+    double extent_cells = 0.0;  // bounding-box extent in level-0 cells
+    k->dev.n_fine = 0;
 
     // bounding box
     double* d_box = nullptr;
@@ -847,6 +891,7 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         h0 = std::max(h0, 1e-300);
         k->h0 = h0;
         k->dev.inv_h0 = 1.0 / h0;
+        extent_cells = extent / h0;
 
         // levels until one cell spans the whole bounding box, then the brute-force level
         int n_grid = 1;
@@ -896,6 +941,49 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         L.mask = m - 1;
         L.shift = l;
         L.h = k->h0 * std::ldexp(1.0, l);
+        L.inv_h = k->dev.inv_h0;
+        L.slot_ordered = l == 0 ? 1 : 0;
+        const double cover = kRingSafety * L.h;
+        L.cover2 = cover * cover;
+        if (l == 0) {
+            // crowded cells? (sources that are far from evenly spaced: the poles of a regular
+            // lat-lon grid) — then build levels finer than h0 for the queries that land there
+            unsigned int* d_max = reinterpret_cast<unsigned int*>(d_scratch);
+            KNN_CUDA(cudaMemset(d_max, 0, 4));
+            max_bucket_kernel<<<std::min((m + 255u) / 256u, 1024u), 256>>>(d_start, m, d_max);
+            KNN_CUDA(cudaGetLastError());
+            unsigned int c_max = 0;
+            KNN_CUDA(cudaMemcpy(&c_max, d_max, 4, cudaMemcpyDeviceToHost));
+            int n_fine = 0;
+            if (c_max > 64)
+                while (n_fine < kMaxFine && (c_max >> (2 * n_fine)) > 16) ++n_fine;
+            // the finest integer cell coordinates must stay well inside int32
+            while (n_fine > 0 && extent_cells * std::ldexp(1.0, n_fine) > 5.0e8) --n_fine;
+            k->dev.n_fine = n_fine;
+        }
+    }
+    for (int j = 0; j < k->dev.n_fine; ++j) {
+        int32_t* d_start = nullptr;
+        int32_t* d_perm = nullptr;
+        KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_start), (static_cast<size_t>(m0) + 2) * 4));
+        KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&d_perm), static_cast<size_t>(n) * 4));
+        const double inv_h = k->dev.inv_h0 * std::ldexp(1.0, j + 1);
+        KNN_CUDA(cudaMemset(d_counts, 0, (static_cast<size_t>(m0) + 2) * 4));
+        bucket_count_kernel<<<pt_blocks, 256>>>(k->d_x, k->d_y, k->d_z, n, k->dev.ox, k->dev.oy, k->dev.oz, inv_h, 0,
+                                               m0 - 1, d_counts, d_bucket_of);
+        KNN_CUDA(cudaGetLastError());
+        KNN_TRY(exclusive_scan(d_counts, m0, d_start, d_scratch, nullptr));
+        KNN_CUDA(cudaMemset(d_counts, 0, (static_cast<size_t>(m0) + 2) * 4));
+        bucket_scatter_kernel<<<pt_blocks, 256>>>(d_bucket_of, n, d_start, d_counts, d_perm);
+        KNN_CUDA(cudaGetLastError());
+        KnnLevel& L = k->dev.fine[j];
+        L.start = d_start;
+        L.perm = d_perm;
+        L.mask = m0 - 1;
+        L.shift = 0;
+        L.h = k->h0 * std::ldexp(1.0, -(j + 1));
+        L.inv_h = inv_h;
+        L.slot_ordered = 0;
         const double cover = kRingSafety * L.h;
         L.cover2 = cover * cover;
     }
@@ -907,6 +995,8 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         L.shift = -1;
         L.cover2 = INFINITY;
         L.h = INFINITY;
+        L.inv_h = k->dev.inv_h0;
+        L.slot_ordered = 0;
     }
     k->dev.x = k->d_x;
     k->dev.y = k->d_y;
@@ -1163,9 +1253,11 @@ extern "C" int at_ball_mark(const at_knn_t* k, const double* qx, const double* q
     if (nq == 0) return AT_OK;  // an empty query set has null pointers (zero-length device arrays)
     AT_REQUIRE(qx != nullptr && qy != nullptr && qz != nullptr && mark != nullptr, "at_ball_mark: null argument");
     const double r2 = r * r;
+    // the finest level (fine levels included, index -1 - j) whose ring-1 covers the radius
     int level = k->dev.n_levels - 1;
-    for (int l = 0; l < k->dev.n_levels; ++l) {
-        if (r2 < k->dev.lv[l].cover2) {
+    for (int l = -k->dev.n_fine; l < k->dev.n_levels; ++l) {
+        const KnnLevel& L = l < 0 ? k->dev.fine[-1 - l] : k->dev.lv[l];
+        if (r2 < L.cover2) {
             level = l;
             break;
         }
