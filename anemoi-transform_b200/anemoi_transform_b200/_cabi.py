@@ -55,6 +55,26 @@ class EpiCol(Structure):
     _fields_ = [("lo", c_double), ("hi", c_double), ("pressure", c_double), ("flags", c_uint32), ("reserved", c_uint32)]
 
 
+class GribInfo(Structure):
+    """`at_grib_field_t`: packing parameters and the location of the packed values of one message."""
+
+    _fields_ = [
+        ("edition", c_int32),
+        ("bits_per_value", c_int32),
+        ("binary_scale", c_int32),
+        ("decimal_scale", c_int32),
+        ("has_bitmap", c_int32),
+        ("reserved", c_int32),
+        ("reference_value", c_double),
+        ("n_points", c_int64),
+        ("n_values", c_int64),
+        ("data_offset", c_int64),
+        ("data_length", c_int64),
+        ("bitmap_offset", c_int64),
+        ("message_length", c_int64),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/at_b200.h one to one
 PROTOTYPES = {
     "at_last_error": (c_char_p, []),
@@ -97,6 +117,13 @@ PROTOTYPES = {
     "at_hostio_regrid": (
         c_int,
         [c_void_p, c_int, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int64, c_int64, c_int, c_void_p, c_int64, POINTER(c_void_p), c_void_p, POINTER(c_int64)],
+    ),
+    "at_grib_scan": (c_int, [c_void_p, c_size_t, POINTER(GribInfo)]),
+    "at_grib_unpack": (c_int, [c_void_p, POINTER(c_int64), POINTER(GribInfo), c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "at_hostio_upload_grib": (c_int, [c_void_p, POINTER(c_void_p), POINTER(GribInfo), c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
+    "at_hostio_regrid_grib": (
+        c_int,
+        [c_void_p, c_int, c_void_p, c_void_p, c_int64, POINTER(c_void_p), POINTER(GribInfo), c_int64, c_int64, c_int, c_void_p, c_int64, POINTER(c_void_p), c_void_p, POINTER(c_int64)],
     ),
     "at_knn_create": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_double, POINTER(c_void_p)]),
     "at_knn_destroy": (c_int, [c_void_p]),

@@ -746,9 +746,12 @@ class StreamedRegrid:
         torch = require_cuda()
         if not (keep_resident or to_host):
             raise ValueError("StreamedRegrid: nothing to produce")
-        n = len(arrays)
-        n_src = int(arrays[0].size)
-        x_np = arrays[0].dtype
+        # `arrays` is either the fields' host values or a grib.PackedFields (messages decoded on
+        # the device: at_hostio_regrid_grib)
+        packed = arrays if hasattr(arrays, "infos") else None
+        n = packed.n_fields if packed is not None else len(arrays)
+        n_src = packed.n_points if packed is not None else int(arrays[0].size)
+        x_np = packed.dtype if packed is not None else arrays[0].dtype
         y_np = np.dtype(np.float32 if y_dtype == torch.float32 else np.float64)
         self._io = HostIO.get()
         self._keep = (arrays, csr, index)  # alive until the native call returns
@@ -772,13 +775,13 @@ class StreamedRegrid:
         self._ticket = c_int64(-1)
         self._error: BaseException | None = None
         args = (
-            "at_hostio_regrid",
+            "at_hostio_regrid_grib" if packed is not None else "at_hostio_regrid",
             self._io.handle,
             int(op),
             csr.handle if csr is not None else None,
             _ptr(index),
             int(n_tgt),
-            _pointer_array(arrays),
+            *((packed.pointers, packed.infos) if packed is not None else (_pointer_array(arrays),)),
             n,
             n_src,
             AT_F32 if x_np == np.float32 else AT_F64,

@@ -23,6 +23,7 @@ from typing import Any
 import numpy as np
 
 from ... import ekd
+from ... import grib
 from ...batching import fields_to_batch
 from ... import _cabi
 from ...device import CsrMatrix, DeviceBatch, StreamedRegrid, gather_rows, require_cuda, results_are_host_bound
@@ -156,6 +157,18 @@ class _BatchedInterpolator:
         torch = require_cuda()
         self.prepare(fields[0])
         out: list[Any] = [None] * len(fields)
+        packed = grib.packed_of(fields)
+        if packed is not None:
+            # simple-packed GRIB messages: the packed octets cross PCIe, the device decodes them
+            # to float64 (what `to_numpy()` of a GRIB field returns) in front of the transform
+            op, csr, index, n_tgt, y_dtype = self.stream_spec(packed.n_points, torch.float64)
+            keep = 8 * n_tgt * len(fields) <= self.memory_fraction * _free_device_bytes()
+            job = StreamedRegrid(op, csr, index, n_tgt, y_dtype, packed, keep_resident=keep, to_host=True)
+            try:
+                self._wrap(fields, list(range(len(fields))), job.batch, out)
+            finally:
+                job.join()
+            return out
         values = [self._host_values(f) for f in fields]
         by_dtype: dict[Any, list[int]] = {}
         for i, v in enumerate(values):
@@ -186,6 +199,14 @@ class _BatchedInterpolator:
         from ...fields import device_column_of
 
         out: list[Any] = [None] * len(fields)
+        if all(device_column_of(f) is None for f in fields):
+            packed = grib.packed_of(fields)
+            if packed is not None:  # decoded on the device, see _regrid_streamed
+                result = self.apply(grib.upload(packed))
+                if results_are_host_bound():
+                    result.prefetch()
+                self._wrap(fields, list(range(len(fields))), result, out)
+                return out
         by_dtype: dict[Any, list[int]] = {}
         host_values: dict[int, np.ndarray] = {}
         for i, f in enumerate(fields):

@@ -27,7 +27,7 @@ from typing import Any
 
 import numpy as np
 
-from . import _cabi
+from . import _cabi, grib
 from .batching import fields_to_batch
 from .device import DeviceBatch, Epilogue, require_cuda, results_are_host_bound, round_up
 from .fields import DeviceColumnField, NewMetadataField, device_column_of, new_field_from_latitudes_longitudes, new_fieldlist_from_list
@@ -227,6 +227,8 @@ class FusedRegrid(Filter):
         for f in fields:
             col = device_column_of(f)
             dt = col[0].data.dtype if col is not None else None
+            if dt is None and grib.is_packed_message(f):
+                dt = torch.float64  # decoded on the device to what to_numpy() gives; no host decode here
             if dt is None:
                 dt = torch.float32 if np.asarray(f.to_numpy()).dtype == np.float32 else torch.float64
             if dt != torch.float32:

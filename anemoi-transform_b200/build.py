@@ -24,7 +24,7 @@ INCLUDE = ROOT / "include"
 LIB_DIR = HERE / "anemoi_transform_b200" / "lib"
 LIB_PATH = LIB_DIR / "libat_b200.so"
 
-SOURCES = ["misc.cu", "spmm.cu", "layout.cu", "knn.cu", "masks.cu", "pipeline.cu", "hostio.cu", "hostcopy.cpp", "matrix.cu"]
+SOURCES = ["misc.cu", "spmm.cu", "layout.cu", "knn.cu", "masks.cu", "pipeline.cu", "hostio.cu", "hostcopy.cpp", "matrix.cu", "grib.cu"]
 
 NVCC_FLAGS = [
     "-gencode",

@@ -31,6 +31,7 @@
 #include <unistd.h>
 
 #include "common.cuh"
+#include "grib.cuh"
 #include "hostcopy.h"
 
 using namespace at;
@@ -475,6 +476,62 @@ int upload_chunk(at_hostio* io, const void* const* fields, const uint8_t* pinned
     return AT_OK;
 }
 
+// The packed-message variant of upload_chunk: only the packed values of each field (data_length
+// octets, 2 bytes per point at 16 bits) are staged and cross PCIe; the slot starts with the
+// table of kernel parameters, and grib_unpack_kernel takes the place of the pack transposition.
+size_t grib_table_bytes(int nf) { return round_up(static_cast<size_t>(nf) * sizeof(GribColumn), 4096); }
+
+size_t grib_chunk_bytes(const at_grib_field_t* infos, int nf) {
+    size_t bytes = grib_table_bytes(nf);
+    for (int f = 0; f < nf; ++f) bytes += round_up(static_cast<size_t>(std::max<int64_t>(infos[f].data_length, 0)) + 16, kAlign);
+    return bytes;
+}
+
+int upload_chunk_grib(at_hostio* io, const void* const* messages, const at_grib_field_t* infos, int nf, int64_t n_points,
+                      int x_dtype, void* d_pm, int64_t ld, cudaStream_t st) {
+    const int slot = static_cast<int>(io->in_seq++ % kSlots);
+    AT_CUDA_TRY(cudaEventSynchronize(io->in_free[slot]));  // the unpack that last read this slot
+    char* const h = io->h_in[slot];
+    char* const d = io->d_in[slot];
+    GribColumn* table = reinterpret_cast<GribColumn*>(h);
+    struct Task {
+        int f;
+        size_t off, len;
+    };
+    std::vector<Task> tasks;
+    std::vector<size_t> base(static_cast<size_t>(nf));
+    size_t cursor = grib_table_bytes(nf);
+    for (int f = 0; f < nf; ++f) {
+        base[static_cast<size_t>(f)] = cursor;
+        const int rc = grib_column_of(infos[f], n_points, static_cast<int64_t>(cursor), &table[f]);
+        if (rc != AT_OK) return rc;
+        // what the kernel reads: the packed values of n_points points (the section may be padded)
+        const size_t len = static_cast<size_t>((n_points * infos[f].bits_per_value + 7) / 8);
+        for (size_t o = 0; o < len; o += kPiece) tasks.push_back({f, o, std::min(kPiece, len - o)});
+        cursor += round_up(len + 16, kAlign);
+    }
+    if (cursor > io->in_slot_bytes) return set_error(AT_ERR_INVALID, "hostio grib upload: chunk of %zu bytes exceeds the slot (%zu)", cursor, io->in_slot_bytes);
+    cudaStream_t s_in = io->s_in;
+    AT_CUDA_TRY(cudaMemcpyAsync(d, h, static_cast<size_t>(nf) * sizeof(GribColumn), cudaMemcpyHostToDevice, s_in));
+    std::atomic<int> err{static_cast<int>(cudaSuccess)};
+    io->workers->parallel_for(static_cast<int64_t>(tasks.size()), [&](int64_t i) {
+        const Task& t = tasks[static_cast<size_t>(i)];
+        const char* src = static_cast<const char*>(messages[t.f]) + infos[t.f].data_offset + t.off;
+        const size_t at = base[static_cast<size_t>(t.f)] + t.off;
+        copy_streaming(h + at, src, t.len);
+        const cudaError_t e = cudaMemcpyAsync(d + at, h + at, t.len, cudaMemcpyHostToDevice, s_in);
+        if (e != cudaSuccess) err.store(static_cast<int>(e));
+    });
+    if (err.load() != static_cast<int>(cudaSuccess))
+        return set_error(AT_ERR_CUDA, "hostio grib upload: %s", cudaGetErrorString(static_cast<cudaError_t>(err.load())));
+    AT_CUDA_TRY(cudaEventRecord(io->h2d_done[slot], s_in));
+    AT_CUDA_TRY(cudaStreamWaitEvent(st, io->h2d_done[slot], 0));
+    const int rc = grib_unpack_launch(reinterpret_cast<const uint8_t*>(d), reinterpret_cast<const GribColumn*>(d), nf, n_points, x_dtype, d_pm, ld, st);
+    if (rc != AT_OK) return rc;
+    AT_CUDA_TRY(cudaEventRecord(io->in_free[slot], st));
+    return AT_OK;
+}
+
 struct PendingHostCopy {
     int slot = -1, nf = 0;
     void* const* dst = nullptr;
@@ -736,10 +793,11 @@ extern "C" int at_hostio_wait(at_hostio_t* io, int64_t ticket) {
     return AT_OK;
 }
 
-extern "C" int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, const int64_t* gather_idx,
-                                int64_t n_out_points, const void* const* fields_in, int64_t n_fields, int64_t n_src,
-                                int x_dtype, void* d_Y, int64_t ldy, void* const* fields_out, void* consumer_stream,
-                                int64_t* ticket) {
+// `grib` != nullptr: fields_in are whole GRIB messages and grib[f] their scans (at_hostio_regrid_grib).
+static int regrid_impl(at_hostio_t* io, int op, const at_csr_t* csr, const int64_t* gather_idx,
+                       int64_t n_out_points, const void* const* fields_in, const at_grib_field_t* grib, int64_t n_fields, int64_t n_src,
+                       int x_dtype, void* d_Y, int64_t ldy, void* const* fields_out, void* consumer_stream,
+                       int64_t* ticket) {
     AT_REQUIRE(io != nullptr && fields_in != nullptr, "at_hostio_regrid: null argument");
     AT_REQUIRE(op == AT_HOSTIO_SPMM || op == AT_HOSTIO_GATHER, "at_hostio_regrid: unknown op %d", op);
     AT_REQUIRE(x_dtype == AT_F32 || x_dtype == AT_F64, "at_hostio_regrid: bad dtype code");
@@ -773,11 +831,19 @@ extern "C" int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, co
     const int xe = x_dtype == AT_F32 ? 4 : 8, ye = y_dtype == AT_F32 ? 4 : 8;
     const size_t in_fb = static_cast<size_t>(n_src) * xe, in_stride = round_up(std::max<size_t>(in_fb, 1), kAlign);
     const size_t out_fb = static_cast<size_t>(n_tgt) * ye, out_stride = round_up(std::max<size_t>(out_fb, 1), kAlign);
-    const int64_t chunk = chunk_fields(n_fields, std::max(in_stride, out_stride), 4);
-    const Classified cin = classify(fields_in, n_fields);
+    size_t packed_stride = 0;  // largest packed field (+ its share of the parameter table)
+    if (grib != nullptr)
+        for (int64_t f = 0; f < n_fields; ++f)
+            packed_stride = std::max(packed_stride, round_up(static_cast<size_t>(std::max<int64_t>(grib[f].data_length, 0)) + 16, kAlign) + sizeof(GribColumn));
+    // a chunk is bounded by the slots (what crosses PCIe) and by its decoded [points x fields] batch
+    const size_t bound_stride = grib != nullptr ? std::max({packed_stride, out_stride, in_stride / 4}) : std::max(in_stride, out_stride);
+    const int64_t chunk = chunk_fields(n_fields, bound_stride, 4);
+    Classified cin;
+    if (grib == nullptr) cin = classify(fields_in, n_fields);
     Classified cout;
     if (fields_out) cout = classify(fields_out, n_fields);
-    int rc = ensure_in_slots(io, static_cast<size_t>(chunk) * in_stride, !cin.all_pinned);
+    int rc = grib != nullptr ? ensure_in_slots(io, static_cast<size_t>(chunk) * packed_stride + 8192, true)
+                             : ensure_in_slots(io, static_cast<size_t>(chunk) * in_stride, !cin.all_pinned);
     if (rc != AT_OK) return rc;
     if (fields_out) {
         rc = ensure_out_slots(io, static_cast<size_t>(chunk) * out_stride, !cout.all_pinned);
@@ -797,7 +863,8 @@ extern "C" int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, co
     PendingHostCopy pending, next;
     for (int64_t c0 = 0; c0 < n_fields; c0 += chunk) {
         const int nf = static_cast<int>(std::min<int64_t>(chunk, n_fields - c0));
-        rc = upload_chunk(io, fields_in + c0, cin.pinned.data() + c0, nf, n_src, xe, in_stride, io->d_x, chunk, sc);
+        rc = grib != nullptr ? upload_chunk_grib(io, fields_in + c0, grib + c0, nf, n_src, x_dtype, io->d_x, chunk, sc)
+                             : upload_chunk(io, fields_in + c0, cin.pinned.data() + c0, nf, n_src, xe, in_stride, io->d_x, chunk, sc);
         if (rc != AT_OK) return rc;
         char* y = d_Y != nullptr ? static_cast<char*>(d_Y) + static_cast<size_t>(c0) * ye : io->d_y;
         const int64_t y_ld = d_Y != nullptr ? ldy : chunk;
@@ -825,5 +892,48 @@ extern "C" int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, co
     }
     if (cin.any_pinned) AT_CUDA_TRY(cudaStreamSynchronize(io->s_in));
     if (fields_out != nullptr && cout.all_pinned && n_tgt > 0) return new_ticket(io, io->s_out, ticket);
+    return AT_OK;
+}
+
+extern "C" int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, const int64_t* gather_idx,
+                                int64_t n_out_points, const void* const* fields_in, int64_t n_fields, int64_t n_src,
+                                int x_dtype, void* d_Y, int64_t ldy, void* const* fields_out, void* consumer_stream,
+                                int64_t* ticket) {
+    return regrid_impl(io, op, csr, gather_idx, n_out_points, fields_in, nullptr, n_fields, n_src, x_dtype, d_Y, ldy, fields_out,
+                       consumer_stream, ticket);
+}
+
+extern "C" int at_hostio_regrid_grib(at_hostio_t* io, int op, const at_csr_t* csr, const int64_t* gather_idx,
+                                     int64_t n_out_points, const void* const* messages, const at_grib_field_t* fields,
+                                     int64_t n_fields, int64_t n_src, int x_dtype, void* d_Y, int64_t ldy,
+                                     void* const* fields_out, void* consumer_stream, int64_t* ticket) {
+    AT_REQUIRE(fields != nullptr || n_fields == 0, "at_hostio_regrid_grib: null scans");
+    return regrid_impl(io, op, csr, gather_idx, n_out_points, messages, fields, n_fields, n_src, x_dtype, d_Y, ldy, fields_out,
+                       consumer_stream, ticket);
+}
+
+extern "C" int at_hostio_upload_grib(at_hostio_t* io, const void* const* messages, const at_grib_field_t* fields,
+                                     int64_t n_fields, int64_t n_points, int x_dtype, void* d_pm, int64_t ld, void* stream) {
+    AT_REQUIRE(io != nullptr && d_pm != nullptr, "at_hostio_upload_grib: null argument");
+    AT_REQUIRE(x_dtype == AT_F32 || x_dtype == AT_F64, "at_hostio_upload_grib: bad dtype code");
+    AT_REQUIRE(n_fields >= 0 && n_points >= 0 && ld >= n_fields, "at_hostio_upload_grib: bad sizes");
+    if (n_fields == 0 || n_points == 0) return AT_OK;
+    AT_REQUIRE(messages != nullptr && fields != nullptr, "at_hostio_upload_grib: null argument");
+    for (int64_t f = 0; f < n_fields; ++f) AT_REQUIRE(messages[f] != nullptr, "at_hostio_upload_grib: message %lld is null", (long long)f);
+    std::lock_guard<std::mutex> lk(io->mu);
+    DeviceGuard guard(io->device);
+    size_t packed_stride = 0;
+    for (int64_t f = 0; f < n_fields; ++f)
+        packed_stride = std::max(packed_stride, round_up(static_cast<size_t>(std::max<int64_t>(fields[f].data_length, 0)) + 16, kAlign) + sizeof(GribColumn));
+    const int64_t chunk = chunk_fields(n_fields, packed_stride, 1);
+    int rc = ensure_in_slots(io, static_cast<size_t>(chunk) * packed_stride + 8192, true);
+    if (rc != AT_OK) return rc;
+    cudaStream_t st = as_stream(stream);
+    const size_t elem = x_dtype == AT_F32 ? 4 : 8;
+    for (int64_t c0 = 0; c0 < n_fields; c0 += chunk) {
+        const int nf = static_cast<int>(std::min<int64_t>(chunk, n_fields - c0));
+        rc = upload_chunk_grib(io, messages + c0, fields + c0, nf, n_points, x_dtype, static_cast<char*>(d_pm) + static_cast<size_t>(c0) * elem, ld, st);
+        if (rc != AT_OK) return rc;
+    }
     return AT_OK;
 }

@@ -330,6 +330,58 @@ AT_API int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, const 
                      int x_dtype, void* d_Y, int64_t ldy, void* const* fields_out, void* consumer_stream,
                      int64_t* ticket);
 
+/* ------------------------------------------------ GRIB simple packing on the device --- */
+/*
+ * A GRIB-backed FieldList reaches RegridFilter.forward as earthkit-data GribFields; the
+ * per-field `field.to_numpy(flatten=True)` of regrid.py:309 (matching.py:242-246 for the
+ * pointwise filters) is where ecCodes decodes each message to float64 on one CPU core.  These
+ * entry points move the packed octets instead (2 bytes per point at 16 bits rather than 8 bytes
+ * of float64) and decode them on the device:
+ *     Y = ((X * 2^E) + R) * 10^-D        (WMO FM 92, regulation 92.9.4; float64, unfused)
+ * Supported: editions 1 and 2, grid-point simple packing (BDS flag 0 / template 5.0),
+ * 0..32 bits per value, ECMWF's long edition-1 messages.  Anything else (second-order, CCSDS,
+ * JPEG, spectral, several fields per message) is AT_ERR_UNSUPPORTED from at_grib_scan and the
+ * caller decodes such fields itself; messages with a bitmap scan fine (has_bitmap = 1) but are
+ * refused by the unpack calls.
+ */
+typedef struct at_grib_field {
+    int32_t edition;        /* 1 | 2 */
+    int32_t bits_per_value; /* 0 = constant field equal to reference_value */
+    int32_t binary_scale;   /* E */
+    int32_t decimal_scale;  /* D */
+    int32_t has_bitmap;
+    int32_t reserved;
+    double reference_value; /* R (IEEE float32 in edition 2, IBM float32 in edition 1) */
+    int64_t n_points;       /* grid points, -1 when the message does not say (edition 1) */
+    int64_t n_values;       /* packed values, -1 when the message does not say */
+    int64_t data_offset;    /* octet offset of the packed values inside the message */
+    int64_t data_length;    /* octets of packed values (padding included) */
+    int64_t bitmap_offset;  /* octet offset of the bitmap, -1 without one */
+    int64_t message_length;
+} at_grib_field_t;
+/* Host only, no CUDA call: parse one message. */
+AT_API int at_grib_scan(const void* message, size_t length, at_grib_field_t* out);
+/*
+ * d_pm[p, f] = value p of field f, f < n_fields: decode packed values that are already in
+ * device memory.  d_packed: device buffer; byte_offsets[f] (host): where field f's packed
+ * values (message + data_offset) start inside it; fields (host): the scans.
+ * out_dtype AT_F64 (what to_numpy gives) or AT_F32 (that value rounded to float32).
+ */
+AT_API int at_grib_unpack(const void* d_packed, const int64_t* byte_offsets, const at_grib_field_t* fields,
+                   int64_t n_fields, int64_t n_points, int out_dtype, void* d_pm, int64_t ld, void* stream);
+/*
+ * at_hostio_upload / at_hostio_regrid for packed fields: messages[f] is the host pointer to
+ * message f (any memory), fields[f] its scan.  Only data_length octets per field are staged and
+ * cross PCIe; the unpack kernel replaces the pack transposition.  x_dtype: the dtype the values
+ * are decoded to (the dtype of the [points x fields] batch the matrix is applied to).
+ */
+AT_API int at_hostio_upload_grib(at_hostio_t* io, const void* const* messages, const at_grib_field_t* fields,
+                          int64_t n_fields, int64_t n_points, int x_dtype, void* d_pm, int64_t ld, void* stream);
+AT_API int at_hostio_regrid_grib(at_hostio_t* io, int op, const at_csr_t* csr, const int64_t* gather_idx,
+                          int64_t n_out_points, const void* const* messages, const at_grib_field_t* fields,
+                          int64_t n_fields, int64_t n_src, int x_dtype, void* d_Y, int64_t ldy,
+                          void* const* fields_out, void* consumer_stream, int64_t* ticket);
+
 /* --------------------------------------------------------------- kNN / masks -------- */
 /*
  * Build the bucketed search structure over source points (float64 xyz, SoA).

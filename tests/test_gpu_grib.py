@@ -1,0 +1,157 @@
+"""GRIB simple packing decoded on the device (csrc/grib.cu) against the numpy oracle, and the
+regrid filter fed with GRIB-backed fields against the same filter fed with the host-decoded
+values.  Bit-exact throughout (float64 decode: one multiply, one add, one multiply)."""
+
+import numpy as np
+import pytest
+from conftest import assert_same_values
+from grib_fields import GribMessageField
+from scipy.sparse import csr_array
+
+from anemoi_transform_b200 import synthetic as syn
+from oracle import grib as ogrib
+
+pytestmark = pytest.mark.gpu
+
+
+def _messages(n_fields, n_points, widths, decimals, editions, seed=0):
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n_fields):
+        nb, d, ed = widths[k % len(widths)], decimals[k % len(decimals)], editions[k % len(editions)]
+        v = rng.normal(280.0, 15.0, n_points) if k % 2 else rng.uniform(-40.0, 40.0, n_points)
+        if nb == 0:
+            v = np.full(n_points, 2.5 * k)
+        out.append((ogrib.encode_grib2 if ed == 2 else ogrib.encode_grib1)(v, max(nb, 1), d))
+    return out
+
+
+def _fields(messages, n_points, lat=None, lon=None):
+    return [GribMessageField(m, n_points, dict(param="t", levelist=850, step=k), latitudes=lat, longitudes=lon) for k, m in enumerate(messages)]
+
+
+@pytest.mark.parametrize("n_points", [1, 7, 8, 255, 256, 1001, 65160])
+def test_every_width_decodes_like_the_oracle(cuda, n_points):
+    from anemoi_transform_b200 import grib
+
+    widths = [0, 1, 3, 7, 8, 11, 12, 13, 16, 20, 24, 28, 31, 32]
+    msgs = _messages(len(widths) * 2, n_points, widths, [0], [2, 2, 1, 1], seed=n_points)
+    want = np.stack([ogrib.decode(m, n_points=n_points) for m in msgs])
+    packed = grib.packed_of(_fields(msgs, n_points))
+    assert packed is not None
+    batch = grib.upload(packed)
+    assert batch.data.dtype == cuda.float64 and batch.n_fields == len(msgs) and batch.n_points == n_points
+    assert_same_values(batch.data[:, : len(msgs)].cpu().numpy().T, want, "float64 decode")
+    as_f32 = grib.upload(packed, np.float32)
+    assert_same_values(as_f32.data[:, : len(msgs)].cpu().numpy().T, want.astype(np.float32), "float32 decode")
+
+
+def test_decimal_scale_factors_and_many_fields(cuda):
+    from anemoi_transform_b200 import grib
+
+    n_points = 40320
+    msgs = _messages(131, n_points, [16, 12, 24, 9], [0, 2, -1, 5, -3], [2, 1], seed=3)
+    want = np.stack([ogrib.decode(m, n_points=n_points) for m in msgs])
+    got = grib.upload(grib.packed_of(_fields(msgs, n_points))).data[:, :131].cpu().numpy().T
+    assert_same_values(got, want, "decimal scale")
+
+
+def test_long_edition1_message(cuda):
+    from anemoi_transform_b200 import grib
+
+    n_points = 4_300_000
+    v = np.random.default_rng(1).normal(101325.0, 900.0, n_points)
+    msg = ogrib.encode_grib1(v, 16, 0)
+    assert len(msg) > 0x800000
+    got = grib.upload(grib.packed_of(_fields([msg], n_points))).data[:, 0].cpu().numpy()
+    assert_same_values(got, ogrib.decode(msg, n_points=n_points), "long GRIB1")
+
+
+def test_raw_unpack_entry_point_validates(cuda):
+    """at_grib_unpack on packed values already in device memory; bad arguments are refused."""
+    import ctypes
+
+    from anemoi_transform_b200 import _cabi, grib
+    from anemoi_transform_b200.device import _ptr, stream_ptr
+
+    n_points = 999
+    msgs = _messages(5, n_points, [16, 10], [0], [2])
+    infos = (_cabi.GribInfo * 5)(*[grib.scan(m) for m in msgs])
+    blob, offs = bytearray(), []
+    for m, i in zip(msgs, infos):
+        while len(blob) % 256:
+            blob.append(0)
+        offs.append(len(blob))
+        blob += m[i.data_offset : i.data_offset + i.data_length]
+    d_blob = cuda.frombuffer(blob, dtype=cuda.uint8).cuda()
+    out = cuda.empty((n_points, 8), dtype=cuda.float64, device="cuda")
+    offsets = (ctypes.c_int64 * 5)(*offs)
+    _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, infos, 5, n_points, _cabi.AT_F64, _ptr(out), 8, stream_ptr())
+    want = np.stack([ogrib.decode(m) for m in msgs])
+    assert_same_values(out[:, :5].cpu().numpy().T, want, "at_grib_unpack")
+    with pytest.raises(ValueError, match="values"):  # the batch has another number of points
+        _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, infos, 5, n_points + 1, _cabi.AT_F64, _ptr(out), 8, stream_ptr())
+    with pytest.raises(ValueError, match="leading dimension"):
+        _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, infos, 5, n_points, _cabi.AT_F64, _ptr(out), 4, stream_ptr())
+    bm = np.random.default_rng(0).uniform(size=n_points) > 0.5
+    with_bitmap = ogrib.encode_grib2(np.arange(float(bm.sum())), 16, 0, bm)
+    one = (_cabi.GribInfo * 1)(grib.scan(with_bitmap))
+    with pytest.raises(ValueError, match="bitmap"):
+        _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, one, 1, n_points, _cabi.AT_F64, _ptr(out), 8, stream_ptr())
+
+
+@pytest.mark.parametrize("mdtype", [np.float32, np.float64])
+def test_regrid_of_grib_fields_equals_regrid_of_decoded_fields(cuda, tmp_path, mdtype):
+    """FieldList of GRIB-backed fields -> RegridFilter.forward -> to_numpy: the packed messages
+    are decoded on the device (no host decode at all) and the result is scipy's `matrix @
+    to_numpy()` bit for bit, streamed and inside a pipeline."""
+    from anemoi_transform_b200 import ekd
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    t_lat, t_lon = syn.octahedral(48)
+    d, i, p, shape = syn.bilinear_matrix(2.0, t_lat, t_lon)
+    d = d.astype(mdtype)
+    s_lat, s_lon = syn.regular_latlon(2.0)
+    path = str(tmp_path / "m.npz")
+    syn.save_regrid_npz(path, d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    m = csr_array((d, i, p), shape=shape)
+    n_src = shape[1]
+    msgs = _messages(37, n_src, [16, 12, 24], [0, 1], [2, 1], seed=11)
+    fields = _fields(msgs, n_src, s_lat, s_lon)
+    want = [m @ ogrib.decode(msg, n_points=n_src) for msg in msgs]
+
+    out = F("regrid", matrix=path).forward(ekd.SimpleFieldList(fields))
+    assert len(out) == 37
+    for k, f in enumerate(out):
+        got = f.to_numpy()
+        assert got.dtype == np.float64
+        assert_same_values(got, want[k], f"streamed field {k}")
+        assert np.array_equal(f.grid_points()[0], t_lat) and f.metadata("step") == k
+    assert sum(f.decodes for f in fields) == 0  # nothing was decoded on the host
+
+    # as the first filter of a pipeline the results stay resident and feed the next filter
+    pipe = F("regrid", matrix=path) | F("rescale", param="t", scale=2.0, offset=1.0)
+    out = pipe.forward(ekd.SimpleFieldList(fields))
+    for k, f in enumerate(out):
+        assert_same_values(f.to_numpy(), want[k] * 2.0 + 1.0, f"pipeline field {k}")
+    assert sum(f.decodes for f in fields) == 0
+
+    # nearest-neighbour regrid: a gather of the decoded values
+    near = F("regrid", method="nearest", in_grid=dict(latitudes=s_lat, longitudes=s_lon), out_grid=dict(latitudes=t_lat, longitudes=t_lon))
+    ref = near.forward(ekd.SimpleFieldList([ekd.ArrayField(ogrib.decode(mm, n_points=n_src), dict(param="t", step=k), latitudes=s_lat, longitudes=s_lon) for k, mm in enumerate(msgs[:5])]))
+    got = near.forward(ekd.SimpleFieldList(fields[:5]))
+    for a, b in zip(got, ref):
+        assert_same_values(a.to_numpy(), b.to_numpy(), "nearest on GRIB fields")
+
+
+def test_grib_fields_of_the_wrong_grid_are_refused(cuda, tmp_path):
+    from anemoi_transform_b200 import ekd
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    t_lat, t_lon = syn.octahedral(48)
+    d, i, p, shape = syn.bilinear_matrix(2.0, t_lat, t_lon)
+    path = str(tmp_path / "m.npz")
+    syn.save_regrid_npz(path, d, i, p, shape, *syn.regular_latlon(2.0), t_lat, t_lon)
+    fields = _fields(_messages(3, shape[1] - 5, [16], [0], [2]), shape[1] - 5)
+    with pytest.raises(ValueError, match="dimension mismatch"):
+        F("regrid", matrix=path).forward(ekd.SimpleFieldList(fields))
