@@ -119,6 +119,7 @@ PROTOTYPES = {
         [c_void_p, c_int, c_void_p, c_void_p, c_int64, POINTER(c_void_p), c_int64, c_int64, c_int, c_void_p, c_int64, POINTER(c_void_p), c_void_p, POINTER(c_int64)],
     ),
     "at_grib_scan": (c_int, [c_void_p, c_size_t, POINTER(GribInfo)]),
+    "at_grib_scan_many": (c_int, [POINTER(c_void_p), POINTER(c_size_t), c_int64, POINTER(GribInfo), POINTER(c_int32)]),
     "at_grib_unpack": (c_int, [c_void_p, POINTER(c_int64), POINTER(GribInfo), c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "at_hostio_upload_grib": (c_int, [c_void_p, POINTER(c_void_p), POINTER(GribInfo), c_int64, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "at_hostio_regrid_grib": (

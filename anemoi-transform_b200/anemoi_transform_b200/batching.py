@@ -47,6 +47,12 @@ def fields_to_batch(fields: Sequence[Any], host_values: Sequence[Any] | None = N
             return DeviceBatch(out, n)
     if host_values is not None and all(v is not None for v in host_values):
         return DeviceBatch.from_host_fields(list(host_values))
+    if all(c is None for c in cols):
+        from . import grib
+
+        packed = grib.packed_of(fields)
+        if packed is not None:  # GRIB messages: packed octets up, decoded on the device
+            return grib.upload(packed)
     return DeviceBatch.from_host_fields([np.asarray(f.to_numpy()).reshape(-1) for f in fields])
 
 

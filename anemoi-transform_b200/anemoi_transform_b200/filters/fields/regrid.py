@@ -161,7 +161,7 @@ class _BatchedInterpolator:
         if packed is not None:
             # simple-packed GRIB messages: the packed octets cross PCIe, the device decodes them
             # to float64 (what `to_numpy()` of a GRIB field returns) in front of the transform
-            op, csr, index, n_tgt, y_dtype = self.stream_spec(packed.n_points, torch.float64)
+            op, csr, index, n_tgt, y_dtype = self.stream_spec(packed.n_points, torch.float32 if packed.dtype == np.float32 else torch.float64)
             keep = 8 * n_tgt * len(fields) <= self.memory_fraction * _free_device_bytes()
             job = StreamedRegrid(op, csr, index, n_tgt, y_dtype, packed, keep_resident=keep, to_host=True)
             try:

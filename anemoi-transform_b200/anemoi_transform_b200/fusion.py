@@ -228,7 +228,8 @@ class FusedRegrid(Filter):
             col = device_column_of(f)
             dt = col[0].data.dtype if col is not None else None
             if dt is None and grib.is_packed_message(f):
-                dt = torch.float64  # decoded on the device to what to_numpy() gives; no host decode here
+                # decoded on the device to what to_numpy() gives; no host decode just to learn the dtype
+                dt = torch.float32 if grib.decode_dtype() == np.float32 else torch.float64
             if dt is None:
                 dt = torch.float32 if np.asarray(f.to_numpy()).dtype == np.float32 else torch.float64
             if dt != torch.float32:

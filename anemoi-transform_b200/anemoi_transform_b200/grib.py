@@ -12,13 +12,18 @@ Wrapper fields (`NewDataField` and friends) forward unknown attributes to the fi
 wrap, so `message()` of a wrapper would return the *original* data; only a `message` defined
 on the field's own class counts.
 
-`AT_B200_GRIB_DEVICE_DECODE=0` switches the packed route off.
+`AT_B200_GRIB_DEVICE_DECODE=0` switches the packed route off.  `AT_B200_GRIB_DTYPE=float32`
+(or `set_decode_dtype(np.float32)`) makes the device write the decoded values as float32 —
+`to_numpy(dtype=np.float32)` instead of `to_numpy()`: the regridded fields then come back as
+float32 when the matrix is float32, half the bytes in HBM and on the way out.  The default is
+float64, what the reference's `to_numpy(flatten=True)` hands to the matrix.
 """
 
 from __future__ import annotations
 
+import math
 import os
-from ctypes import byref, c_void_p
+from ctypes import byref, c_int32, c_size_t, c_void_p
 from typing import Any, Sequence
 
 import numpy as np
@@ -31,16 +36,33 @@ def enabled() -> bool:
     return os.environ.get("AT_B200_GRIB_DEVICE_DECODE", "1") != "0"
 
 
+_decode_dtype: np.dtype | None = None
+
+
+def set_decode_dtype(dtype) -> None:
+    """float64 (default, the reference's `to_numpy()`), float32, or None for the environment's choice."""
+    global _decode_dtype
+    if dtype is not None and np.dtype(dtype) not in (np.dtype(np.float32), np.dtype(np.float64)):
+        raise ValueError("GRIB values decode to float32 or float64")
+    _decode_dtype = None if dtype is None else np.dtype(dtype)
+
+
+def decode_dtype() -> np.dtype:
+    if _decode_dtype is not None:
+        return _decode_dtype
+    return np.dtype(np.float32 if os.environ.get("AT_B200_GRIB_DTYPE", "float64") in ("float32", "f32") else np.float64)
+
+
 def scan(message) -> GribInfo | None:
     """Packing parameters of one message, or None when it is not something the device decodes
     (not GRIB, another packing, several fields).  Host only."""
-    buf = np.frombuffer(message, dtype=np.uint8)
+    return _scan_buffer(np.frombuffer(message, dtype=np.uint8))
+
+
+def _scan_buffer(buf: np.ndarray) -> GribInfo | None:
     info = GribInfo()
-    try:
-        _cabi.call("at_grib_scan", c_void_p(buf.ctypes.data), buf.size, byref(info))
-    except (_cabi.NativeCallError, ValueError):
-        return None
-    return info
+    rc = _cabi.load().at_grib_scan(buf.__array_interface__["data"][0], buf.size, byref(info))
+    return info if rc == _cabi.AT_OK else None
 
 
 def _message_of(field: Any):
@@ -64,23 +86,18 @@ def is_packed_message(field: Any) -> bool:
 class PackedFields:
     """The messages of a FieldList the device can decode, with their scans."""
 
-    def __init__(self, buffers: list[np.ndarray], infos, n_points: int):
+    def __init__(self, buffers: list[np.ndarray], infos, n_points: int, pointers=None):
         self.buffers = buffers  # uint8 views on the messages: keep them alive while in use
         self.infos = infos  # ctypes array of GribInfo
         self.n_points = n_points
         self.n_fields = len(buffers)
-        self.pointers = (c_void_p * self.n_fields)(*[b.ctypes.data for b in buffers])
-
-    #: what `GribField.to_numpy()` returns
-    dtype = np.dtype(np.float64)
+        self.pointers = pointers if pointers is not None else (c_void_p * self.n_fields)(*[b.__array_interface__["data"][0] for b in buffers])
+        #: dtype the device decodes to: float64 = what `GribField.to_numpy()` returns
+        self.dtype = decode_dtype()
 
     @property
     def packed_bytes(self) -> int:
         return int(sum((self.n_points * i.bits_per_value + 7) // 8 for i in self.infos))
-
-    def slice(self, lo: int, hi: int) -> "PackedFields":
-        infos = (GribInfo * (hi - lo))(*self.infos[lo:hi])
-        return PackedFields(self.buffers[lo:hi], infos, self.n_points)
 
 
 def packed_of(fields: Sequence[Any]) -> PackedFields | None:
@@ -88,39 +105,45 @@ def packed_of(fields: Sequence[Any]) -> PackedFields | None:
     without a bitmap, else None (the caller then uses `to_numpy()` for all of them)."""
     if not fields or not enabled():
         return None
+    n = len(fields)
     buffers: list[np.ndarray] = []
-    scans: list[GribInfo] = []
-    n_points = -1
     for f in fields:
         m = _message_of(f)
         if m is None:
             return None
-        info = scan(m)
-        if info is None or info.has_bitmap:
+        buffers.append(np.frombuffer(m, dtype=np.uint8))
+    pointers = (c_void_p * n)(*[b.__array_interface__["data"][0] for b in buffers])
+    lengths = (c_size_t * n)(*[b.size for b in buffers])
+    infos = (GribInfo * n)()
+    status = (c_int32 * n)()
+    _cabi.call("at_grib_scan_many", pointers, lengths, n, infos, status)  # one call: the per-message parse is C
+    if any(status):
+        return None
+    n_points = -1
+    for f, info in zip(fields, infos):
+        if info.has_bitmap:
             return None
-        n = info.n_values if info.n_values >= 0 else info.n_points
+        count = info.n_values if info.n_values >= 0 else info.n_points
         shape = getattr(f, "shape", None)
         if shape is not None:
-            declared = int(np.prod(shape))
-            if n >= 0 and n != declared:
+            declared = math.prod(shape)
+            if count >= 0 and count != declared:
                 return None
-            n = declared
-        if n < 0 or (n_points >= 0 and n != n_points):
+            count = declared
+        if count < 0 or (n_points >= 0 and count != n_points):
             return None
-        if info.data_length < (n * info.bits_per_value + 7) // 8:
+        if info.data_length < (count * info.bits_per_value + 7) // 8:
             return None
-        n_points = n
-        buffers.append(np.frombuffer(m, dtype=np.uint8))
-        scans.append(info)
-    return PackedFields(buffers, (GribInfo * len(scans))(*scans), n_points)
+        n_points = count
+    return PackedFields(buffers, infos, n_points, pointers)
 
 
-def upload(packed: PackedFields, dtype=np.float64):
+def upload(packed: PackedFields, dtype=None):
     """→ `DeviceBatch` holding the decoded fields as columns (`at_hostio_upload_grib`)."""
     from .device import AT_F32, AT_F64, DeviceBatch, HostIO, _ptr, empty_batch, require_cuda, stream_ptr
 
     torch = require_cuda()
-    dtype = np.dtype(dtype)
+    dtype = np.dtype(dtype) if dtype is not None else packed.dtype
     tdtype = torch.float32 if dtype == np.float32 else torch.float64
     pm = empty_batch(packed.n_points, packed.n_fields, tdtype, "cuda")
     _cabi.call(
@@ -138,4 +161,4 @@ def upload(packed: PackedFields, dtype=np.float64):
     return DeviceBatch(pm, packed.n_fields)
 
 
-__all__ = ["GribInfo", "PackedFields", "enabled", "is_packed_message", "packed_of", "scan", "upload"]
+__all__ = ["GribInfo", "PackedFields", "decode_dtype", "enabled", "is_packed_message", "packed_of", "scan", "set_decode_dtype", "upload"]

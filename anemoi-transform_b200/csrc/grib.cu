@@ -348,6 +348,14 @@ extern "C" int at_grib_scan(const void* message, size_t length, at_grib_field_t*
     return set_error(AT_ERR_UNSUPPORTED, "at_grib_scan: GRIB edition %d", edition);
 }
 
+extern "C" int at_grib_scan_many(const void* const* messages, const size_t* lengths, int64_t n, at_grib_field_t* out, int32_t* status) {
+    AT_REQUIRE(n >= 0, "at_grib_scan_many: negative count");
+    if (n == 0) return AT_OK;
+    AT_REQUIRE(messages != nullptr && lengths != nullptr && out != nullptr && status != nullptr, "at_grib_scan_many: null argument");
+    for (int64_t i = 0; i < n; ++i) status[i] = messages[i] != nullptr ? at_grib_scan(messages[i], lengths[i], out + i) : AT_ERR_INVALID;
+    return AT_OK;
+}
+
 extern "C" int at_grib_unpack(const void* d_packed, const int64_t* byte_offsets, const at_grib_field_t* fields, int64_t n_fields,
                               int64_t n_points, int out_dtype, void* d_pm, int64_t ld, void* stream) {
     AT_REQUIRE(n_fields >= 0 && n_points >= 0, "at_grib_unpack: negative size");

@@ -21,6 +21,9 @@ One JSON line on stdout (rank 0):
     pipeline_e2e  config 4 as a FieldList pipeline (regrid | uv_to_ddff | q_to_r | clip |
                   apply_mask, O1280 → N320-shaped, 12 nnz/row), with the reference's five-pass
                   CPU chain timed beside it (N = 1)
+    e2e_grib      config 3 as a GRIB FieldList (16-bit simple packing): packed octets over PCIe,
+                  decoded on the device (float64 like the reference's to_numpy(), and float32),
+                  with the reference's decode + scipy chain timed beside it (N = 1)
     roofline      algorithmic bytes per launch / measured launch time vs the measured HBM peak;
                   `traffic` is read from the committed ncu export under profiles/
     cpu_baseline  the reference's CPU path on the box's host cores (bounded sample; three
@@ -304,6 +307,126 @@ def plugin_e2e(w, matrix_path, n_local: int, steps: int, rank: int, barrier, max
         "path": "create_filter_by_name('regrid', matrix=...).forward(FieldList of pageable numpy fields) + to_numpy() of every output: "
         "worker threads stage the fields into pinned slots -> H2D -> pack -> SpMM -> unpack -> D2H straight into the page-locked arrays the caller receives",
     }
+
+
+class BenchGribField:
+    """A GRIB-backed field as earthkit-data hands it to a filter: it owns the encoded message
+    (`message()`), its `to_numpy()` decodes on the host (here through the oracle, used by the
+    parity check only — the B200 path never calls it)."""
+
+    def __init__(self, message: bytes, n_points: int, md: dict, lat, lon):
+        self._message, self._n, self._md, self._lat, self._lon = message, n_points, md, lat, lon
+
+    shape = property(lambda self: (self._n,))
+
+    def message(self) -> bytes:
+        return self._message
+
+    def to_numpy(self, flatten: bool = False, dtype=None, index=None):
+        from oracle import grib as ogrib
+
+        v = ogrib.decode(self._message, n_points=self._n)
+        return v if dtype is None else v.astype(dtype)
+
+    def metadata(self, *keys, namespace=None, default=None, **kw):
+        if namespace is not None:
+            return dict(self._md) if namespace in ("mars", "default") else {}
+        if not keys:
+            from anemoi_transform_b200 import ekd
+
+            return ekd.Metadata(dict(self._md))
+        vals = [self._md.get(k, default) for k in keys]
+        return vals[0] if len(keys) == 1 else vals
+
+    def grid_points(self):
+        return self._lat, self._lon
+
+
+def grib_e2e(w, matrix_path, n_local: int, steps: int, rank: int, world: int, barrier, max_over_ranks) -> dict | None:
+    """config 3 as a GRIB FieldList: 16-bit simple-packed edition-2 messages in ->
+    RegridFilter.forward -> to_numpy() of every output.  The packed octets cross PCIe and are
+    decoded on the device; results are float64 like the reference's (float32 matrix @ float64
+    values), and float32 with `set_decode_dtype(float32)`."""
+    import gc
+
+    import psutil
+
+    from anemoi_transform_b200 import ekd, grib
+    from anemoi_transform_b200 import synthetic as syn
+    from anemoi_transform_b200.device import pinned_pool_trim
+    from anemoi_transform_b200.filters import create_filter_by_name
+    from oracle import grib as ogrib
+
+    n_tgt, n_src = w["shape"]
+    need = n_local * (2 * n_src + 8 * n_tgt) * 1.5
+    if psutil.virtual_memory().available < need:
+        return None
+    s_lat, s_lon = syn.regular_latlon(0.25)
+    rng = np.random.default_rng(17 + rank)
+    distinct = [ogrib.encode_grib2(rng.normal(280.0, 15.0, n_src), 16, 0) for _ in range(min(32, n_local))]
+    # every field owns its own copy of a message, as a reader would deliver them
+    messages = [bytes(bytearray(distinct[k % len(distinct)])) for k in range(n_local)]
+    fields = [BenchGribField(m, n_src, dict(param="t", levelist=850, step=k), s_lat, s_lon) for k, m in enumerate(messages)]
+    fl = ekd.SimpleFieldList(fields)
+    regrid = create_filter_by_name("regrid", matrix=matrix_path)
+    out = {}
+    for name, dtype in (("float64", None), ("float32", np.float32)):
+        grib.set_decode_dtype(dtype)
+        try:
+            gc.collect()
+            pinned_pool_trim()  # the previous leg's result blocks have another size
+
+            def once():
+                return [f.to_numpy() for f in regrid.forward(fl)]
+
+            arrays = once()
+            del arrays
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                arrays = None
+                arrays = once()
+            seconds = max_over_ranks(time.perf_counter() - t0) / steps
+            parity = None
+            if rank == 0:
+                from scipy.sparse import csr_array
+
+                m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
+                checks = []
+                for f in (0, n_local // 2, n_local - 1):
+                    x = ogrib.decode(messages[f], n_points=n_src)
+                    want = m @ (x if dtype is None else x.astype(dtype))
+                    checks.append(bool(want.dtype == arrays[f].dtype and np.array_equal(want, arrays[f])))
+                parity = all(checks)
+            itemsize = arrays[0].dtype.itemsize
+            del arrays
+            out[name] = {
+                "value": N_FIELDS / seconds,
+                "unit": "fields/s",
+                "ms_per_step": seconds * 1e3,
+                "h2d_bytes_per_step": 2 * N_FIELDS * n_src,
+                "d2h_bytes_per_step": itemsize * N_FIELDS * n_tgt,
+                "parity_spot_check": parity,
+            }
+        finally:
+            grib.set_decode_dtype(None)
+    gc.collect()
+    pinned_pool_trim()
+    result = {
+        "workload": "config 3 as a GRIB FieldList: 3120 edition-2 messages, grid-point simple packing, 16 bits per value, D = 0 (2.08 MB each)",
+        "path": "create_filter_by_name('regrid', matrix=...).forward(FieldList of GRIB-backed fields) + to_numpy() of every output: "
+        "packed octets staged -> H2D -> grib_unpack_kernel (decode + point-major packing) -> SpMM -> unpack -> D2H into page-locked result arrays; no host decode",
+        "decode_float64": out["float64"],
+        "decode_float32": out["float32"],
+    }
+    if rank == 0 and world == 1:
+        from benchmarks.cpu_reference import grib_chain_fields_per_s
+
+        cpu = grib_chain_fields_per_s(w, messages[: 16 * max(1, min(os.cpu_count() or 1, 32))], n_src)
+        result["cpu_chain"] = cpu
+        result["speedup_vs_as_is"] = out["float64"]["value"] / cpu["as_is_fields_per_s"]
+        result["speedup_vs_best_effort"] = out["float64"]["value"] / cpu["best_effort_fields_per_s"]
+    return result
 
 
 def cabi_e2e(csr, w, n_local: int, steps: int, chunk: int, rank: int, world: int, barrier, max_over_ranks) -> dict:
@@ -621,6 +744,9 @@ def run_gpu(args):
         "host_pool_fields": cabi["host_pool_fields"],
     }
 
+    gc.collect()
+    grib_leg = None if args.skip_grib else grib_e2e(w, matrix_path, n_local, max(1, min(2, e2e_steps)), rank, world, barrier, max_over_ranks)
+
     pipe4 = None
     if world == 1 and not args.skip_pipeline:
         gc.collect()
@@ -651,6 +777,7 @@ def run_gpu(args):
             "e2e": e2e,
             "e2e_cabi": e2e_cabi,
             "pipeline_e2e": pipe4,
+            "e2e_grib": grib_leg,
             "gpu_launches": args.steps * world,
             "roofline": {
                 "bound": "hbm",
@@ -697,6 +824,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=64, help="fields per chunk of the C-ABI host pipeline")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--skip-pipeline", action="store_true", help="skip the config-4 pipeline leg")
+    ap.add_argument("--skip-grib", action="store_true", help="skip the GRIB-input leg")
     ap.add_argument("--value-only", action="store_true", help="device-resident leg only (for ncu captures); prints a partial line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 1)

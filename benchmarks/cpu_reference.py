@@ -171,3 +171,73 @@ def pipeline_chain_fields_per_s(m, groups: list[dict], mask_threshold: float = 0
             a[mask] = np.nan
         n_in += 4
     return (n_in + 1) / (time.perf_counter() - t0)
+
+
+# ---- GRIB-backed FieldList: decode + regrid, the reference's forward() on GRIB input ----------
+def _grib_worker_init(data, idx, ptr, shape, messages, n_points):
+    from scipy.sparse import csr_array
+
+    _STATE["m"] = csr_array((data, idx, ptr), shape=shape)
+    _STATE["messages"], _STATE["n_points"] = messages, n_points
+
+
+def _grib_worker_step(span):
+    from oracle import grib as ogrib
+
+    lo, hi = span
+    m, msgs, n = _STATE["m"], _STATE["messages"], _STATE["n_points"]
+    acc = 0.0
+    for k in range(lo, hi):
+        acc += float((m @ ogrib.decode(msgs[k], n_points=n))[0])
+    return acc
+
+
+def grib_chain_fields_per_s(w: dict, messages: list, n_points: int) -> dict:
+    """What `RegridFilter.forward` costs the reference on a GRIB FieldList: per field
+    `to_numpy(flatten=True)` (the message decoded to float64; here the oracle's numpy
+    restatement of the simple-packing decode, 2.4 ms per 0.25-degree field) then
+    `matrix @ values` (scipy, float64) — on one thread as it runs, and over one process per core."""
+    from scipy.sparse import csr_array
+
+    from oracle import grib as ogrib
+
+    m = csr_array((w["data"], w["idx"], w["ptr"]), shape=w["shape"])
+    n = min(len(messages), 32)
+    m @ ogrib.decode(messages[0], n_points=n_points)
+    t0 = time.perf_counter()
+    for k in range(n):
+        m @ ogrib.decode(messages[k], n_points=n_points)
+    as_is = n / (time.perf_counter() - t0)
+    cores = host_cores()
+    procs = max(1, min(cores, len(messages)))
+    per = len(messages) // procs
+    spans = [(p * per, (p + 1) * per) for p in range(procs)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(procs, initializer=_grib_worker_init, initargs=(w["data"], w["idx"], w["ptr"], tuple(w["shape"]), messages, n_points)) as pool:
+        pool.map(_grib_worker_step, spans, chunksize=1)
+        best = float("inf")
+        for _ in range(2):
+            t0 = time.perf_counter()
+            pool.map(_grib_worker_step, spans, chunksize=1)
+            best = min(best, time.perf_counter() - t0)
+    # plain-C port: one-pass decode + csr_matvec per field under OpenMP (what a C decoder like
+    # ecCodes plus scipy's C loop would reach with every core busy)
+    sample = messages[: per * procs]
+    ogrib.c_decode_regrid_f64(w["ptr"], w["idx"], w["data"], sample[:cores], n_points, n_threads=cores)
+    c_best = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        ogrib.c_decode_regrid_f64(w["ptr"], w["idx"], w["data"], sample, n_points, n_threads=cores)
+        c_best = min(c_best, time.perf_counter() - t0)
+    legs = {"scipy_processes": per * procs / best, "c_port_openmp": len(sample) / c_best}
+    return {
+        "as_is_fields_per_s": as_is,
+        "as_is_cores": 1,
+        "best_effort_fields_per_s": max(legs.values()),
+        "best_effort_leg": max(legs, key=legs.get),
+        "best_effort_legs": legs,
+        "best_effort_cores": procs,
+        "sample_fields": per * procs,
+        "what": "per field: simple-packing decode to float64 (what ecCodes does inside to_numpy) + csr @ x in float64 — one thread as the reference runs (numpy decode + scipy), "
+        "and on every core: numpy + scipy over one process per core, and a plain-C one-pass decode + csr_matvec under OpenMP (oracle/csr_matvec.c); the faster is reported",
+    }

@@ -361,6 +361,9 @@ typedef struct at_grib_field {
 } at_grib_field_t;
 /* Host only, no CUDA call: parse one message. */
 AT_API int at_grib_scan(const void* message, size_t length, at_grib_field_t* out);
+/* The same for n messages in one call: status[i] is what at_grib_scan returned for message i. */
+AT_API int at_grib_scan_many(const void* const* messages, const size_t* lengths, int64_t n,
+                      at_grib_field_t* out, int32_t* status);
 /*
  * d_pm[p, f] = value p of field f, f < n_fields: decode packed values that are already in
  * device memory.  d_packed: device buffer; byte_offsets[f] (host): where field f's packed

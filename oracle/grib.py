@@ -340,12 +340,49 @@ def decode(msg: bytes, n_points: int | None = None, missing=np.nan) -> np.ndarra
     if nb == 0:
         vals = np.full(n_values, r, dtype=np.float64)
     else:
-        x = unpack_bits(msg[info["data_offset"] : info["data_offset"] + info["data_length"]], n_values, nb)
         s = power(info["binary_scale"], 2)
         d = power(-info["decimal_scale"], 10)
-        vals = ((x.astype(np.float64) * s) + r) * d
+        if nb in (8, 16, 32):  # whole octets: one pass converts the big-endian integers (exactly)
+            vals = np.frombuffer(msg, dtype={8: ">u1", 16: ">u2", 32: ">u4"}[nb], count=n_values, offset=info["data_offset"]).astype(np.float64)
+        else:
+            vals = unpack_bits(msg[info["data_offset"] : info["data_offset"] + info["data_length"]], n_values, nb).astype(np.float64)
+        vals *= s  # ((X * s) + R) * d, one rounding each, as separate passes
+        vals += r
+        if d != 1.0:  # multiplying by 1.0 changes nothing
+            vals *= d
     if bits is None:
         return vals
     out = np.full(bits.size, missing, dtype=np.float64)
     out[bits] = vals
+    return out
+
+
+# ------------------------------------------------------------------------ C port -------
+def c_decode_regrid_f64(indptr, indices, data, messages: list, n_points: int, n_threads: int = 0) -> np.ndarray:
+    """[F, n_tgt] float64: per message the 16-bit simple-packing decode and `matrix @ values`,
+    fields spread over OpenMP threads (oracle/csr_matvec.c: `oracle_grib16_regrid_f64`) — the
+    multi-core CPU baseline of bench.py's GRIB leg.  Bitwise equal to `matrix @ decode(msg)`."""
+    import ctypes
+
+    from . import spmm as ospmm
+
+    lib = ospmm._c()
+    fn = lib.oracle_grib16_regrid_f64
+    fn.restype = None
+    fn.argtypes = [ctypes.c_int64] + [ctypes.c_void_p] * 8 + [ctypes.c_int64] * 3 + [ctypes.c_int]
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    infos = [scan(m) for m in messages]
+    for i in infos:
+        if i["bits_per_value"] != 16 or i["has_bitmap"]:
+            raise NotImplementedError("the C baseline decodes 16-bit simple packing without a bitmap")
+    views = [np.frombuffer(m, dtype=np.uint8) for m in messages]
+    ptrs = (ctypes.c_void_p * len(messages))(*[v.ctypes.data + i["data_offset"] for v, i in zip(views, infos)])
+    r = np.array([i["reference_value"] for i in infos], dtype=np.float64)
+    s = np.array([power(i["binary_scale"], 2) for i in infos], dtype=np.float64)
+    d = np.array([power(-i["decimal_scale"], 10) for i in infos], dtype=np.float64)
+    n_tgt = indptr.shape[0] - 1
+    out = np.empty((len(messages), n_tgt), dtype=np.float64)
+    fn(n_tgt, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, ptrs, r.ctypes.data, s.ctypes.data, d.ctypes.data, out.ctypes.data, len(messages), n_points, n_tgt, int(n_threads))
     return out

@@ -155,3 +155,36 @@ def test_grib_fields_of_the_wrong_grid_are_refused(cuda, tmp_path):
     fields = _fields(_messages(3, shape[1] - 5, [16], [0], [2]), shape[1] - 5)
     with pytest.raises(ValueError, match="dimension mismatch"):
         F("regrid", matrix=path).forward(ekd.SimpleFieldList(fields))
+
+
+def test_float32_decode_feeds_the_fused_pipeline(cuda, tmp_path):
+    """`set_decode_dtype(float32)`: values leave the unpack kernel as float32 (what
+    `to_numpy(dtype=float32)` gives), a float32 matrix then returns float32 fields and the
+    regrid | pointwise pipeline runs as ONE fused launch on GRIB input, with no host decode."""
+    from anemoi_transform_b200 import ekd, grib
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    t_lat, t_lon = syn.octahedral(48)
+    d, i, p, shape = syn.bilinear_matrix(2.0, t_lat, t_lon)
+    s_lat, s_lon = syn.regular_latlon(2.0)
+    path = str(tmp_path / "m.npz")
+    syn.save_regrid_npz(path, d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    m = csr_array((d, i, p), shape=shape)
+    n_src = shape[1]
+    msgs = _messages(8, n_src, [16], [0], [2], seed=4)
+    fields = _fields(msgs, n_src, s_lat, s_lon)
+    x32 = [ogrib.decode(mm, n_points=n_src).astype(np.float32) for mm in msgs]
+    grib.set_decode_dtype(np.float32)
+    try:
+        out = F("regrid", matrix=path).forward(ekd.SimpleFieldList(fields))
+        for k, f in enumerate(out):
+            got = f.to_numpy()
+            assert got.dtype == np.float32
+            assert_same_values(got, m @ x32[k], f"float32 field {k}")
+        pipe = F("regrid", matrix=path) | F("clip_fields", param="t", minimum=250.0, maximum=290.0)
+        out = pipe.forward(ekd.SimpleFieldList(fields))
+        for k, f in enumerate(out):
+            assert_same_values(f.to_numpy(), np.clip(m @ x32[k], np.float32(250.0), np.float32(290.0)), f"fused field {k}")
+    finally:
+        grib.set_decode_dtype(None)
+    assert sum(f.decodes for f in fields) == 0

@@ -157,3 +157,19 @@ def test_only_fields_that_own_a_message_take_the_packed_route(native_library):
         assert grib.packed_of([f]) is None
     finally:
         del os.environ["AT_B200_GRIB_DEVICE_DECODE"]
+
+
+def test_c_decode_regrid_equals_numpy_decode_then_scipy():
+    from scipy.sparse import csr_array
+
+    from anemoi_transform_b200 import synthetic as syn
+
+    t_lat, t_lon = syn.octahedral(24)
+    d, i, p, shape = syn.bilinear_matrix(2.0, t_lat, t_lon)
+    m = csr_array((d, i, p), shape=shape)
+    rng = np.random.default_rng(2)
+    msgs = [ogrib.encode_grib2(rng.normal(280, 15, shape[1]), 16, dec) for dec in (0, 0, 2, -1, 0)]
+    got = ogrib.c_decode_regrid_f64(p, i, d, msgs, shape[1], n_threads=3)
+    for k, msg in enumerate(msgs):
+        want = m @ ogrib.decode(msg)
+        assert want.dtype == np.float64 and np.array_equal(got[k], want)
