@@ -39,20 +39,22 @@ struct KnnLevel {
     double cover2;         // (kRingSafety · h_l)²: every source closer than this was scanned
     double h;              // cell edge h0 · 2^l
     double inv_h;          // scale of the integer cell coordinates before `shift` (1/h0, or 1/h of a fine level)
-    int slot_ordered;      // sx/sy/sz follow this level's slots (level 0 only)
+    const double *sx, *sy, *sz;  // sources in this level's slot order (coalesced candidate reads), or nullptr
 };
+
+// Levels that get their own slot-ordered copy of the coordinates: the ones a query may start at
+// (level 0 for k = 1, level 1 for k <= 6, level 2 beyond — see start_level()).
+constexpr int kSlotOrderedLevels = 3;
 
 // Fine levels: cell edges h0/2, h0/4, … built only when some level-0 cell is crowded (a regular
 // lat-lon grid packs 1440 points into every ring around the poles, and 1440 copies of the pole
 // itself).  They are not part of the octree the far search walks; a query whose level-0 ring is
 // crowded starts at the fine level where that ring shrinks to ≈ 100 candidates.
 constexpr int kMaxFine = 4;
-constexpr int kDenseRing = 256;    // level-0 ring sizes above this try the fine levels first
-constexpr int kDenseTarget = 128;  // candidates a fine ring should hold
+constexpr int kDenseTarget = 64;  // candidates a ring should hold at least before a query goes below its start level (x4: when it does)
 
 struct KnnDev {
     const double *x, *y, *z;     // sources, original order
-    const double *sx, *sy, *sz;  // sources in level-0 slot order (coalesced candidate reads)
     long long n;
     double ox, oy, oz;  // grid origin
     double inv_h0;
@@ -366,8 +368,8 @@ __device__ __forceinline__ int ring_slot(const Ring& r, int t) {
 }
 
 // Load candidate at slot s of level L.
-__device__ __forceinline__ void load_cand(const KnnDev& d, const KnnLevel& L, bool level0, int s,
-                                          double& px, double& py, double& pz, long long& idx) {
+__device__ __forceinline__ void load_cand(const KnnDev& d, const KnnLevel& L, int s, double& px, double& py, double& pz,
+                                          long long& idx) {
     if (L.perm == nullptr) {
         idx = s;
         px = d.x[s];
@@ -375,10 +377,10 @@ __device__ __forceinline__ void load_cand(const KnnDev& d, const KnnLevel& L, bo
         pz = d.z[s];
     } else {
         idx = __ldg(L.perm + s);
-        if (level0) {
-            px = __ldg(d.sx + s);
-            py = __ldg(d.sy + s);
-            pz = __ldg(d.sz + s);
+        if (L.sx != nullptr) {
+            px = __ldg(L.sx + s);
+            py = __ldg(L.sy + s);
+            pz = __ldg(L.sz + s);
         } else {
             px = __ldg(d.x + idx);
             py = __ldg(d.y + idx);
@@ -389,7 +391,7 @@ __device__ __forceinline__ void load_cand(const KnnDev& d, const KnnLevel& L, bo
 
 // One selection pass over the ring: smallest key strictly greater than (prev_d2, prev_idx)
 // with d2 < ub2.  Returns the warp-wide minimum (d2 = +inf when none).
-__device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, bool level0, const Ring& r,
+__device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, const Ring& r,
                                             double qx, double qy, double qz, double prev_d2,
                                             long long prev_idx, double ub2, int lane) {
     Cand best;
@@ -402,7 +404,7 @@ __device__ __forceinline__ Cand select_next(const KnnDev& d, const KnnLevel& L, 
         if (t < r.total && s >= 0) {
             double px, py, pz;
             long long idx;
-            load_cand(d, L, level0, s, px, py, pz, idx);
+            load_cand(d, L, s, px, py, pz, idx);
             const double c2 = dist2(qx, qy, qz, px, py, pz);
             if (c2 < ub2 && key_less(prev_d2, prev_idx, c2, idx) && key_less(c2, idx, best.d2, best.idx)) {
                 best.d2 = c2;
@@ -424,7 +426,7 @@ struct CandCache {
     int* idx;
 };
 
-__device__ __forceinline__ void fill_cache(const KnnDev& d, const KnnLevel& L, bool level0, const Ring& r, double qx,
+__device__ __forceinline__ void fill_cache(const KnnDev& d, const KnnLevel& L, const Ring& r, double qx,
                                            double qy, double qz, double ub2, int lane, const CandCache& c) {
     for (int t0 = 0; t0 < r.total; t0 += 32) {
         const int t = t0 + lane;
@@ -434,7 +436,7 @@ __device__ __forceinline__ void fill_cache(const KnnDev& d, const KnnLevel& L, b
             long long idx = d.n;
             if (s >= 0) {
                 double px, py, pz;
-                load_cand(d, L, level0, s, px, py, pz, idx);
+                load_cand(d, L, s, px, py, pz, idx);
                 c2 = dist2(qx, qy, qz, px, py, pz);
                 if (!(c2 < ub2)) c2 = INFINITY;
             }
@@ -463,28 +465,38 @@ __device__ __forceinline__ Cand select_cached(const KnnDev& d, const CandCache& 
     return best;
 }
 
+// Level a search for k neighbours starts at: the ring of level l (cell edge h0·2^l, h0 = the mean
+// point spacing) is sure to hold every source within h0·2^l, a disc of about pi·4^l points.
+__host__ __device__ inline int start_level(int k, int n_grid_levels) {
+    const int want = k <= 1 ? 0 : (k <= 6 ? 1 : 2);
+    return want < n_grid_levels ? want : (n_grid_levels > 0 ? n_grid_levels - 1 : 0);
+}
+
 // Full k-NN of one query by one warp.  Lane j < k ends up holding the j-th neighbour.
 // Returns tie bits (valid when want_tie).
 //
-// Only the first `max_levels` levels are tried; `done` tells whether the answer is final
-// (the caller hands unfinished queries to the tree search).
+// The search starts at `first_level` (start_level(k)) — lower, down into the fine levels, when
+// that ring is crowded — and tries levels below `max_levels`; `done` tells whether the answer
+// is final (the caller hands unfinished queries to the tree search).
 template <bool CACHE>
 __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double qy, double qz, int k,
-                                            double ub2, bool want_tie, int lane, int max_levels, bool& done,
+                                            double ub2, bool want_tie, int lane, int first_level, int max_levels, bool& done,
                                             double& my_d2, long long& my_idx, const CandCache& cache) {
     unsigned tie = 0;
     done = true;
-    // Crowded neighbourhood (warp-uniform: the ring total is the same in every lane): start at
-    // the fine level where the ring holds about kDenseTarget candidates and walk back up.
-    int first = 0;
+    // Crowded neighbourhood (warp-uniform: the ring total is the same in every lane): go down to
+    // the level where the ring holds about `target` candidates and walk back up from there.
+    int first = first_level;
     Ring r0;
     r0.s0 = r0.cnt = r0.off = r0.total = 0;
-    if (d.n_fine > 0 && max_levels > 0) {
-        r0 = ring_ranges(d, d.lv[0], qx, qy, qz, lane);
-        if (r0.total > kDenseRing) {
+    const bool can_descend = (d.n_fine > 0 || first_level > 0) && first_level < max_levels;
+    if (can_descend) {
+        r0 = ring_ranges(d, d.lv[first_level], qx, qy, qz, lane);
+        const int target = max(kDenseTarget, 16 * k);
+        if (r0.total > 4 * target) {
             int halvings = 1;  // each halving of the cell edge divides a surface ring by about 4
-            while (halvings < d.n_fine && (r0.total >> (2 * halvings)) > kDenseTarget) ++halvings;
-            first = -halvings;
+            while (first_level - halvings > -d.n_fine && (r0.total >> (2 * halvings)) > target) ++halvings;
+            first = first_level - halvings;
         }
     }
     for (int level = first; level < max_levels; ++level) {
@@ -492,7 +504,7 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         const bool last = level == d.n_levels - 1;
         // A level whose ring cannot decide anything (cover radius below the best possible
         // distance) is still scanned: cheap, and usually terminates at level 0.
-        const Ring r = (level == 0 && d.n_fine > 0) ? r0 : ring_ranges(d, L, qx, qy, qz, lane);
+        const Ring r = (level == first_level && can_descend) ? r0 : ring_ranges(d, L, qx, qy, qz, lane);
         my_d2 = INFINITY;
         my_idx = d.n;
         tie = 0;
@@ -501,10 +513,10 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         long long pidx = -1;
         int found = 0;
         const bool cached = CACHE && k > 1 && r.total <= kCandCap;  // warp-uniform
-        if (cached) fill_cache(d, L, L.slot_ordered != 0, r, qx, qy, qz, ub2, lane, cache);
+        if (cached) fill_cache(d, L, r, qx, qy, qz, ub2, lane, cache);
         for (int j = 0; j < k; ++j) {
             const Cand c = cached ? select_cached(d, cache, r.total, pd2, pidx, lane)
-                                  : select_next(d, L, L.slot_ordered != 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+                                  : select_next(d, L, r, qx, qy, qz, pd2, pidx, ub2, lane);
             if (!(c.d2 < INFINITY)) break;
             if (j > 0 && c.d2 == pd2) tie |= 1u;
             if (lane == j) {
@@ -519,7 +531,7 @@ __device__ __forceinline__ unsigned knn_one(const KnnDev& d, double qx, double q
         if (complete || last || ub2 <= L.cover2) {
             if (want_tie && found == k) {
                 const Cand c = cached ? select_cached(d, cache, r.total, pd2, pidx, lane)
-                                      : select_next(d, L, L.slot_ordered != 0, r, qx, qy, qz, pd2, pidx, ub2, lane);
+                                      : select_next(d, L, r, qx, qy, qz, pd2, pidx, ub2, lane);
                 if (c.d2 == pd2) tie |= 2u;
             }
             __syncwarp();  // the cache is rewritten by the next level / query
@@ -544,11 +556,14 @@ struct PeerOut {
 
 // CACHE: k > 1, candidate keys cached in shared memory (knn_one); PEERS: also store to peers
 template <bool CACHE, bool PEERS>
-__global__ void __launch_bounds__(256, CACHE ? 4 : 5)
+__global__ void __launch_bounds__(256, 4)
     knn_query_kernel(const KnnDev d, const double* __restrict__ qx, const double* __restrict__ qy,
-                     const double* __restrict__ qz, long long nq, int k, double ub2, int near_levels,
+                     const double* __restrict__ qz, long long nq, int k, double ub2, int first_level, int near_levels,
                      long long* __restrict__ idx_out, double* __restrict__ dist_out,
-                     uint8_t* __restrict__ tie_out, const PeerOut peers) {
+                     uint8_t* __restrict__ tie_out, const PeerOut peers, const int* __restrict__ list,
+                     const unsigned int* __restrict__ list_n) {
+    // `list` != nullptr: only the *list_n queries named there (what knn1_thread_kernel left over)
+    if (list != nullptr) nq = *list_n;
     // per-warp candidate cache (k > 1 only; the k = 1 launch passes no shared memory)
     extern __shared__ __align__(16) unsigned char s_cache[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -562,12 +577,13 @@ __global__ void __launch_bounds__(256, CACHE ? 4 : 5)
         // Grids run pole to pole, and a regular lat-lon source is crowded at both poles: the
         // expensive queries sit at the two ends of the array.  Taking the queries from both ends
         // inwards starts them first, so they overlap the cheap ones instead of forming the tail.
-        const long long q = (w & 1) ? nq - 1 - (w >> 1) : (w >> 1);
+        long long q = (w & 1) ? nq - 1 - (w >> 1) : (w >> 1);
+        if (list != nullptr) q = list[q];
         const double x = qx[q], y = qy[q], z = qz[q];
         double d2;
         long long idx;
         bool done;
-        const unsigned tie = knn_one<CACHE>(d, x, y, z, k, ub2, tie_out != nullptr, lane, near_levels, done, d2, idx, cache);
+        const unsigned tie = knn_one<CACHE>(d, x, y, z, k, ub2, tie_out != nullptr, lane, first_level, near_levels, done, d2, idx, cache);
         if (!done) {
             if (lane == 0) idx_out[q * k] = kPending;
             continue;
@@ -579,6 +595,120 @@ __global__ void __launch_bounds__(256, CACHE ? 4 : 5)
                 for (int p = 0; p < peers.n; ++p) peers.ptr[p][q * k + lane] = idx;
         }
         if (tie_out != nullptr && lane == 0) tie_out[q] = static_cast<uint8_t>(tie);
+    }
+}
+
+// ---- k = 1, one THREAD per query ------------------------------------------------------------
+// With about one source per level-0 cell a ring holds a dozen candidates: a warp per query spends
+// its instructions on the ring bookkeeping (27 hashes spread over lanes, a scan, a slot search, a
+// warp reduction — 446 warp instructions per query) rather than on distances.  Here a thread
+// walks the 27 cells of its own query and keeps the smallest key (d², index) — the same exact
+// answer, the minimum does not depend on the order — at a fraction of the issue slots.
+// Consecutive queries are neighbours on the sphere, so the lanes of a warp read the same buckets
+// (L1 hits).  Level 0 keeps, for this kernel, one {start, end} pair per bucket (one 8-byte load)
+// and one 32-byte record {x, y, z, index} per source in slot order (one sector per candidate).
+// A query whose ring is crowded (more than kThreadRingMax candidates: the poles of a regular
+// lat-lon grid) or whose nearest source is not inside the level-0 cover radius is appended to
+// `pending` and finished by knn_query_kernel, one warp per query, with its fine and coarse levels.
+// (Letting each warp finish its own leftovers instead put up to 32 crowded queries in sequence
+// on the polar warps: 0.36 ms against 0.19 + 0.06 ms for the two kernels.)
+constexpr int kThreadRingMax = 96;
+
+struct __align__(32) KnnRecord {
+    double x, y, z;
+    long long idx;
+};
+
+template <bool PEERS>
+__global__ void __launch_bounds__(256)
+    knn1_thread_kernel(const KnnDev d, const int2* __restrict__ range0, const KnnRecord* __restrict__ rec0,
+                       const double* __restrict__ qx, const double* __restrict__ qy, const double* __restrict__ qz,
+                       long long nq, double ub2, long long* __restrict__ idx_out, double* __restrict__ dist_out,
+                       const PeerOut peers, int* __restrict__ pending, unsigned int* __restrict__ n_pending) {
+    const KnnLevel& L = d.lv[0];
+    const int lane = threadIdx.x & 31;
+    const long long n_blocks32 = (nq + 31) >> 5;
+    const long long wi = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (wi >= n_blocks32) return;
+    // blocks of 32 consecutive queries taken from both ends of the array inwards (the crowded
+    // poles first, see knn_query_kernel)
+    const long long b32 = (wi & 1) ? n_blocks32 - 1 - (wi >> 1) : (wi >> 1);
+    const long long q = (b32 << 5) + lane;
+    bool leftover = false;
+    if (q < nq) {
+        const double x = qx[q], y = qy[q], z = qz[q];
+        const int cx = cell_coord(x, d.ox, L.inv_h), cy = cell_coord(y, d.oy, L.inv_h), cz = cell_coord(z, d.oz, L.inv_h);
+        double best = INFINITY;
+        long long best_idx = 0x7fffffffffffffffll;
+        int scanned = 0;
+#pragma unroll 1
+        for (int dz = -1; dz <= 1 && scanned <= kThreadRingMax; ++dz) {
+            // the nine buckets of this plane of cells: all lookups in flight together, then ONE
+            // loop over their candidates (a loop per bucket left most lanes idle: lanes disagree
+            // on which buckets are empty, the warp ran the sum of the per-bucket maxima)
+            int first[9], upto[9];  // slot offset and cumulative count per bucket (registers: fully unrolled)
+            int total = 0;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) {
+                const int2 r = __ldg(range0 + (cell_hash(cx + (c % 3) - 1, cy + (c / 3) - 1, cz + dz) & L.mask));
+                first[c] = r.x - total;  // slot = first[c] + i for the candidates i of bucket c
+                total += r.y - r.x;
+                upto[c] = total;
+            }
+            scanned += total;
+            if (scanned > kThreadRingMax) break;
+            for (int i = 0; i < total; ++i) {
+                int base = first[0];
+#pragma unroll
+                for (int c = 1; c < 9; ++c) base = i >= upto[c - 1] ? first[c] : base;
+                const int s = base + i;
+                const double2 xy = __ldg(reinterpret_cast<const double2*>(rec0 + s));
+                const double2 zi = __ldg(reinterpret_cast<const double2*>(rec0 + s) + 1);
+                const double c2 = dist2(x, y, z, xy.x, xy.y, zi.x);
+                const long long idx = __double_as_longlong(zi.y);
+                // (a bucket shared by two cells is read twice: same key, no change)
+                if (c2 < ub2 && (c2 < best || (c2 == best && idx < best_idx))) {
+                    best = c2;
+                    best_idx = idx;
+                }
+            }
+        }
+        const bool decided = scanned <= kThreadRingMax && (best < L.cover2 || ub2 <= L.cover2);
+        if (decided) {
+            const long long found = best < INFINITY ? best_idx : d.n;
+            idx_out[q] = found;
+            if (dist_out != nullptr) dist_out[q] = sqrt(best);
+            if (PEERS)
+                for (int p = 0; p < peers.n; ++p) peers.ptr[p][q] = found;
+        } else {
+            leftover = true;
+        }
+    }
+    // warp-aggregated append to the list of queries the warp kernel finishes
+    const unsigned who = __ballot_sync(0xffffffffu, leftover);
+    if (who != 0) {
+        unsigned base = 0;
+        if (lane == __ffs(who) - 1) base = atomicAdd(n_pending, __popc(who));
+        base = __shfl_sync(0xffffffffu, base, __ffs(who) - 1);
+        if (leftover) pending[base + __popc(who & ((1u << lane) - 1u))] = static_cast<int>(q);
+    }
+}
+
+// Level-0 tables of knn1_thread_kernel, built once per index.
+__global__ void knn_level0_tables_kernel(const int32_t* __restrict__ start, const int32_t* __restrict__ perm,
+                                         const double* __restrict__ x, const double* __restrict__ y,
+                                         const double* __restrict__ z, uint32_t n_buckets, long long n,
+                                         int2* __restrict__ range0, KnnRecord* __restrict__ rec0) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_buckets) range0[i] = make_int2(start[i], start[i + 1]);
+    if (i < n) {
+        const int s = perm[i];
+        KnnRecord r;
+        r.x = x[s];
+        r.y = y[s];
+        r.z = z[s];
+        r.idx = s;
+        rec0[i] = r;
     }
 }
 
@@ -639,7 +769,7 @@ __global__ void __launch_bounds__(128)
             for (int s = s0; s < s1; ++s) {
                 double px, py, pz;
                 long long idx;
-                load_cand(d, L, level == 0, s, px, py, pz, idx);
+                load_cand(d, L, s, px, py, pz, idx);
                 const double c2 = dist2(x, y, z, px, py, pz);
                 if (!(c2 < ub2)) continue;
                 if (cnt == kk && !key_less(c2, idx, bd[kk - 1], bi[kk - 1])) continue;
@@ -716,7 +846,7 @@ __global__ void __launch_bounds__(256)
         long long idx;
         bool done;
         const CandCache no_cache = {nullptr, nullptr};
-        knn_one<false>(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, d.n_levels, done, d2, idx, no_cache);
+        knn_one<false>(d, d.x[q], d.y[q], d.z[q], 2, INFINITY, false, lane, start_level(2, d.n_levels - 1), d.n_levels, done, d2, idx, no_cache);
         const double second = __shfl_sync(0xffffffffu, d2, 1);
         best = fmin(best, second);
     }
@@ -743,7 +873,7 @@ __global__ void __launch_bounds__(256)
             if (t < r.total && s >= 0) {
                 double px, py, pz;
                 long long idx;
-                load_cand(d, L, L.slot_ordered != 0, s, px, py, pz, idx);
+                load_cand(d, L, s, px, py, pz, idx);
                 if (dist2(x, y, z, px, py, pz) <= r2) mark[idx] = 1;
             }
         }
@@ -759,11 +889,17 @@ struct at_knn {
     double* d_x = nullptr;
     double* d_y = nullptr;
     double* d_z = nullptr;
-    double* d_sx = nullptr;
-    double* d_sy = nullptr;
-    double* d_sz = nullptr;
     std::vector<void*> owned;  // every device allocation, for destroy
     at::KnnDev dev;
+    // level-0 tables of the one-thread-per-query kernel (k = 1): {start, end} per bucket and a
+    // 32-byte {x, y, z, index} record per source in slot order
+    int2* d_range0 = nullptr;
+    at::KnnRecord* d_rec0 = nullptr;
+    // scratch of the k = 1 query: ids of the queries the thread kernel leaves to the warp kernel,
+    // and their count (grown on demand; queries on one index are issued one at a time)
+    int* d_pending = nullptr;
+    unsigned int* d_n_pending = nullptr;
+    long long pending_cap = 0;
 };
 
 using namespace at;
@@ -790,6 +926,8 @@ double dec_ordered(unsigned long long u) {
 
 extern "C" int at_knn_destroy(at_knn_t* k) {
     if (k == nullptr) return AT_OK;
+    if (k->d_pending != nullptr) device_free(k->d_pending);
+    if (k->d_n_pending != nullptr) device_free(k->d_n_pending);
     for (void* p : k->owned) device_free(p);
     delete k;
     return AT_OK;
@@ -885,7 +1023,9 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
             // A surface crossing a cubic lattice occupies ~1.5 cells per hc² of area.
             const double area = std::max(1.0, static_cast<double>(occ)) * hc * hc / 1.5;
             const double spacing = std::sqrt(area / static_cast<double>(n));
-            h0 = 2.0 * spacing;
+            // one point per cell on average: a k = 1 query reads ~11 candidates in its ring;
+            // larger k start one or two levels up (start_level), where the cells are 2x / 4x this
+            h0 = 1.0 * spacing;
         }
         h0 = std::max(h0, extent / 1.0e6);  // keeps level-0 integer coordinates small
         h0 = std::max(h0, 1e-300);
@@ -899,14 +1039,12 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         k->dev.n_levels = n_grid + 1;
     }
 
-    // sorted copies for level 0
-    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_sx), nb));
-    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_sy), nb));
-    KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_sz), nb));
-
     // bucket tables
+    // Four buckets per point at level 0 (about one point per cell there) and a quarter of that
+    // per level up, like the cells: colliding cells share a bucket, and at one bucket per cell
+    // every ring read twice the candidates it needed (and overflowed the k > 1 cache).
     uint32_t m0 = 1024;
-    while (m0 < static_cast<uint64_t>(n) && m0 < (1u << 26)) m0 <<= 1;
+    while (m0 < 4 * static_cast<uint64_t>(n) && m0 < (1u << 26)) m0 <<= 1;
     int32_t* d_bucket_of = nullptr;
     int32_t* d_counts = nullptr;
     int32_t* d_scratch = nullptr;
@@ -930,22 +1068,33 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         KNN_CUDA(cudaMemset(d_counts, 0, (static_cast<size_t>(m) + 2) * 4));
         bucket_scatter_kernel<<<pt_blocks, 256>>>(d_bucket_of, n, d_start, d_counts, d_perm);
         KNN_CUDA(cudaGetLastError());
-        if (l == 0) {
-            permute_points_kernel<<<pt_blocks, 256>>>(k->d_x, k->d_y, k->d_z, d_perm, n, k->d_sx, k->d_sy,
-                                                     k->d_sz);
-            KNN_CUDA(cudaGetLastError());
-        }
         KnnLevel& L = k->dev.lv[l];
+        L.sx = L.sy = L.sz = nullptr;
+        if (l < kSlotOrderedLevels) {  // coordinates in this level's slot order: coalesced candidate reads
+            double *sx = nullptr, *sy = nullptr, *sz = nullptr;
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&sx), nb));
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&sy), nb));
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&sz), nb));
+            permute_points_kernel<<<pt_blocks, 256>>>(k->d_x, k->d_y, k->d_z, d_perm, n, sx, sy, sz);
+            KNN_CUDA(cudaGetLastError());
+            L.sx = sx;
+            L.sy = sy;
+            L.sz = sz;
+        }
         L.start = d_start;
         L.perm = d_perm;
         L.mask = m - 1;
         L.shift = l;
         L.h = k->h0 * std::ldexp(1.0, l);
         L.inv_h = k->dev.inv_h0;
-        L.slot_ordered = l == 0 ? 1 : 0;
         const double cover = kRingSafety * L.h;
         L.cover2 = cover * cover;
         if (l == 0) {
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_range0), static_cast<size_t>(m) * sizeof(int2)));
+            KNN_TRY(dev_alloc(k, reinterpret_cast<void**>(&k->d_rec0), static_cast<size_t>(n) * sizeof(KnnRecord)));
+            const long long items = std::max<long long>(m, n);
+            knn_level0_tables_kernel<<<static_cast<unsigned>((items + 255) / 256), 256>>>(d_start, d_perm, k->d_x, k->d_y, k->d_z, m, n, k->d_range0, k->d_rec0);
+            KNN_CUDA(cudaGetLastError());
             // crowded cells? (sources that are far from evenly spaced: the poles of a regular
             // lat-lon grid) — then build levels finer than h0 for the queries that land there
             unsigned int* d_max = reinterpret_cast<unsigned int*>(d_scratch);
@@ -983,7 +1132,7 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         L.shift = 0;
         L.h = k->h0 * std::ldexp(1.0, -(j + 1));
         L.inv_h = inv_h;
-        L.slot_ordered = 0;
+        L.sx = L.sy = L.sz = nullptr;
         const double cover = kRingSafety * L.h;
         L.cover2 = cover * cover;
     }
@@ -996,14 +1145,11 @@ extern "C" int at_knn_create(const double* x, const double* y, const double* z, 
         L.cover2 = INFINITY;
         L.h = INFINITY;
         L.inv_h = k->dev.inv_h0;
-        L.slot_ordered = 0;
+        L.sx = L.sy = L.sz = nullptr;
     }
     k->dev.x = k->d_x;
     k->dev.y = k->d_y;
     k->dev.z = k->d_z;
-    k->dev.sx = k->d_sx;
-    k->dev.sy = k->d_sy;
-    k->dev.sz = k->d_sz;
     k->dev.n = n;
     KNN_CUDA(cudaDeviceSynchronize());
 #undef KNN_TRY
@@ -1025,18 +1171,45 @@ static int launch_knn_query(const at_knn_t* k, const double* qx, const double* q
     // near search: ring 1 of the two finest levels, one warp per query; whatever it cannot
     // decide (queries far from every source) goes to the per-thread tree search
     const int n_grid = k->dev.n_levels - 1;
-    const int near_levels = std::min(2, n_grid);
+    const int first_level = start_level(kk, n_grid);
+    const int near_levels = std::min(first_level + 2, n_grid);  // exclusive
     // k > 1: 8 warps x kCandCap cached keys (float64 d2 + int32 index) = 48 KB per CTA
     const size_t cache_bytes = kk > 1 ? static_cast<size_t>(8) * kCandCap * (sizeof(double) + sizeof(int)) : 0;
     const unsigned blocks = query_blocks(nq);
+    const int* list = nullptr;
+    const unsigned int* list_n = nullptr;
+    unsigned list_blocks = blocks;
+    if (kk == 1 && tie_out == nullptr && k->d_range0 != nullptr && nq < (1ll << 31) - 64) {
+        // one thread per query first; the warp kernel then finishes what that left over
+        at_knn* mk = const_cast<at_knn*>(k);
+        if (mk->pending_cap < nq) {
+            if (mk->d_pending != nullptr) device_free(mk->d_pending);
+            mk->d_pending = nullptr;
+            mk->pending_cap = 0;
+            AT_CUDA_TRY(device_alloc(reinterpret_cast<void**>(&mk->d_pending), static_cast<size_t>(nq) * sizeof(int)));
+            mk->pending_cap = nq;
+        }
+        if (mk->d_n_pending == nullptr) AT_CUDA_TRY(device_alloc(reinterpret_cast<void**>(&mk->d_n_pending), 16));
+        AT_CUDA_TRY(cudaMemsetAsync(mk->d_n_pending, 0, sizeof(unsigned int), st));
+        const long long threads = ((nq + 31) / 32) * 32;
+        const unsigned tblocks = static_cast<unsigned>((threads + 255) / 256);
+        if (peers.n > 0)
+            knn1_thread_kernel<true><<<tblocks, 256, 0, st>>>(k->dev, k->d_range0, k->d_rec0, qx, qy, qz, nq, ub2, idx_out, dist_out, peers, mk->d_pending, mk->d_n_pending);
+        else
+            knn1_thread_kernel<false><<<tblocks, 256, 0, st>>>(k->dev, k->d_range0, k->d_rec0, qx, qy, qz, nq, ub2, idx_out, dist_out, peers, mk->d_pending, mk->d_n_pending);
+        AT_LAUNCH_CHECK("knn1_thread_kernel");
+        list = mk->d_pending;
+        list_n = mk->d_n_pending;
+        list_blocks = std::min(blocks, static_cast<unsigned>(sm_count()) * 8u);  // grid-stride over *list_n
+    }
     if (kk > 1 && peers.n > 0)
-        knn_query_kernel<true, true><<<blocks, 256, cache_bytes, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
+        knn_query_kernel<true, true><<<blocks, 256, cache_bytes, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, first_level, near_levels, idx_out, dist_out, tie_out, peers, nullptr, nullptr);
     else if (kk > 1)
-        knn_query_kernel<true, false><<<blocks, 256, cache_bytes, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
+        knn_query_kernel<true, false><<<blocks, 256, cache_bytes, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, first_level, near_levels, idx_out, dist_out, tie_out, peers, nullptr, nullptr);
     else if (peers.n > 0)
-        knn_query_kernel<false, true><<<blocks, 256, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
+        knn_query_kernel<false, true><<<list_blocks, 256, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, first_level, near_levels, idx_out, dist_out, tie_out, peers, list, list_n);
     else
-        knn_query_kernel<false, false><<<blocks, 256, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, near_levels, idx_out, dist_out, tie_out, peers);
+        knn_query_kernel<false, false><<<list_blocks, 256, 0, st>>>(k->dev, qx, qy, qz, nq, kk, ub2, first_level, near_levels, idx_out, dist_out, tie_out, peers, list, list_n);
     AT_LAUNCH_CHECK("knn_query_kernel");
     const long long tree_blocks = (nq + 127) / 128;
     AT_REQUIRE(tree_blocks < (1ll << 31), "at_knn_query: too many queries");
