@@ -55,6 +55,12 @@ def run_epilogue(kind: int, inputs: Sequence[Any], out_cols: Sequence[tuple], ro
     if batch is not None:
         return _run_uniform(kind, inputs, out_cols, row_mask, pa, pb, batch)
     cols = [device_column_of(f) for f in inputs]
+    if inputs and all(c is None for c in cols):
+        from ... import grib
+
+        packed = grib.packed_of(inputs)
+        if packed is not None:  # GRIB messages: decoded on the device, one dtype for all, no host decode
+            return _run_uniform(kind, inputs, out_cols, row_mask, pa, pb, grib.upload(packed))
     values = [None if c is not None else np.asarray(f.to_numpy()).reshape(-1) for f, c in zip(inputs, cols)]
     dtypes = [_float_dtype(numpy_dtype_of(c[0]) if c is not None else v.dtype) for c, v in zip(cols, values)]
     g_in = 2 if kind in PAIR_KINDS else 1

@@ -157,21 +157,23 @@ class _BatchedInterpolator:
         torch = require_cuda()
         self.prepare(fields[0])
         out: list[Any] = [None] * len(fields)
-        packed = grib.packed_of(fields)
+        packed, packed_idx, other_idx = grib.split(fields)
         if packed is not None:
             # simple-packed GRIB messages: the packed octets cross PCIe, the device decodes them
             # to float64 (what `to_numpy()` of a GRIB field returns) in front of the transform
             op, csr, index, n_tgt, y_dtype = self.stream_spec(packed.n_points, torch.float32 if packed.dtype == np.float32 else torch.float64)
-            keep = 8 * n_tgt * len(fields) <= self.memory_fraction * _free_device_bytes()
+            keep = 8 * n_tgt * len(packed_idx) <= self.memory_fraction * _free_device_bytes()
             job = StreamedRegrid(op, csr, index, n_tgt, y_dtype, packed, keep_resident=keep, to_host=True)
             try:
-                self._wrap(fields, list(range(len(fields))), job.batch, out)
+                self._wrap(fields, packed_idx, job.batch, out)
             finally:
                 job.join()
-            return out
-        values = [self._host_values(f) for f in fields]
+            if not other_idx:
+                return out
+        # everything else (numpy fields, other packings, bitmaps): values fetched on the host
+        values: dict[int, np.ndarray] = {i: self._host_values(fields[i]) for i in other_idx}
         by_dtype: dict[Any, list[int]] = {}
-        for i, v in enumerate(values):
+        for i, v in values.items():
             by_dtype.setdefault(v.dtype, []).append(i)
         for dtype, idxs in by_dtype.items():
             arrays = [values[i] for i in idxs]

@@ -138,6 +138,35 @@ def packed_of(fields: Sequence[Any]) -> PackedFields | None:
     return PackedFields(buffers, infos, n_points, pointers)
 
 
+def split(fields: Sequence[Any]) -> tuple[PackedFields | None, list[int], list[int]]:
+    """Partition a FieldList: (the messages the device decodes, their positions, the positions of
+    the fields that keep the `to_numpy()` route — other packings, bitmaps, wrappers, numpy fields)."""
+    if not fields or not enabled():
+        return None, [], list(range(len(fields)))
+    candidates = [i for i, f in enumerate(fields) if _message_of(f) is not None]
+    if not candidates:
+        return None, [], list(range(len(fields)))
+    whole = packed_of(fields) if len(candidates) == len(fields) else None
+    if whole is not None:
+        return whole, list(range(len(fields))), []
+    # field by field: keep those that scan as simple packing without a bitmap and share the size
+    # of the first such field
+    keep: list[int] = []
+    n_points = -1
+    for i in candidates:
+        one = packed_of([fields[i]])
+        if one is not None and (n_points < 0 or one.n_points == n_points):
+            n_points = one.n_points
+            keep.append(i)
+    if not keep:
+        return None, [], list(range(len(fields)))
+    packed = packed_of([fields[i] for i in keep])
+    if packed is None:  # pragma: no cover - each member was accepted on its own
+        return None, [], list(range(len(fields)))
+    kept = set(keep)
+    return packed, keep, [i for i in range(len(fields)) if i not in kept]
+
+
 def upload(packed: PackedFields, dtype=None):
     """→ `DeviceBatch` holding the decoded fields as columns (`at_hostio_upload_grib`)."""
     from .device import AT_F32, AT_F64, DeviceBatch, HostIO, _ptr, empty_batch, require_cuda, stream_ptr
@@ -161,4 +190,4 @@ def upload(packed: PackedFields, dtype=None):
     return DeviceBatch(pm, packed.n_fields)
 
 
-__all__ = ["GribInfo", "PackedFields", "decode_dtype", "enabled", "is_packed_message", "packed_of", "scan", "set_decode_dtype", "upload"]
+__all__ = ["GribInfo", "PackedFields", "decode_dtype", "enabled", "is_packed_message", "packed_of", "scan", "set_decode_dtype", "split", "upload"]

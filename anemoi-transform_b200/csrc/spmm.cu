@@ -24,6 +24,8 @@
 //     __fmul_rn / __fadd_rn (never contracted to FMA);
 //   - Y is write-once: streaming stores (st.global.cs).
 #include <algorithm>
+#include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -930,6 +932,71 @@ extern "C" int at_spmm(const at_csr_t* csr, const void* X, int x_dtype, int64_t 
 }
 
 // ---- epilogue handle --------------------------------------------------------------------
+// The cubic tables of es(T) (epilogue.cuh): float64 formulas sampled at four Chebyshev points of
+// every 0.5 K interval, interpolating cubic in f = (t - node) / 0.5, rounded to float32.  Once per
+// device and process.
+namespace {
+
+double es_mixed_f64(double t) {
+    // thresholds as the float32 numbers numpy compares a float32 field with (NEP 50)
+    const double t0 = static_cast<double>(273.16f), ti = static_cast<double>(250.16f);
+    const double es_w = 611.21 * std::exp(17.502 * (t - 273.16) / (t - 32.19));
+    const double es_i = 611.21 * std::exp(22.587 * (t - 273.16) / (t + 0.7));
+    if (t <= ti) return es_i;
+    if (t >= t0) return es_w;
+    const double a = (t - 250.16) / 23.0;
+    return a * a * es_w + (1.0 - a * a) * es_i;
+}
+
+double es_water_f64(double t) { return 611.21 * std::exp(17.502 * (t - 273.16) / (t - 32.19)); }
+
+void fit_es_table(double (*fn)(double), float4* out) {
+    const double pi = 3.14159265358979323846;
+    double f[4];
+    for (int k = 0; k < 4; ++k) f[k] = 0.5 * (1.0 - std::cos((2 * k + 1) * pi / 8.0));
+    for (int j = 0; j < kEsTableN; ++j) {
+        const double node = static_cast<double>(kEsTableT) + 0.5 * (j - kEsTableZero);
+        // Newton divided differences through the four points, expanded to monomials in f
+        double dd[4];
+        for (int k = 0; k < 4; ++k) dd[k] = fn(node + 0.5 * f[k]);
+        for (int level = 1; level < 4; ++level)
+            for (int k = 3; k >= level; --k) dd[k] = (dd[k] - dd[k - 1]) / (f[k] - f[k - level]);
+        // p(x) = dd0 + dd1 (x-f0) + dd2 (x-f0)(x-f1) + dd3 (x-f0)(x-f1)(x-f2)
+        double c[4] = {dd[3], 0, 0, 0};  // Horner from the top: coefficients of the running polynomial, highest first
+        int deg = 0;
+        for (int k = 2; k >= 0; --k) {  // poly = poly * (x - f[k]) + dd[k]
+            double nc[4] = {0, 0, 0, 0};
+            for (int i = 0; i <= deg; ++i) {
+                nc[i] += c[i];
+                nc[i + 1] -= c[i] * f[k];
+            }
+            ++deg;
+            nc[deg] += dd[k];
+            for (int i = 0; i < 4; ++i) c[i] = nc[i];
+        }
+        // c[0..3] = coefficients of x^3, x^2, x^1, x^0
+        out[j] = make_float4(static_cast<float>(c[3]), static_cast<float>(c[2]), static_cast<float>(c[1]), static_cast<float>(c[0]));
+    }
+}
+
+int ensure_es_tables() {
+    static std::mutex mu;
+    static std::vector<int> ready;  // devices whose tables are loaded
+    int dev = 0;
+    AT_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (std::find(ready.begin(), ready.end(), dev) != ready.end()) return AT_OK;
+    std::vector<float4> mixed(kEsTableN), water(kEsTableN);
+    fit_es_table(es_mixed_f64, mixed.data());
+    fit_es_table(es_water_f64, water.data());
+    AT_CUDA_TRY(cudaMemcpyToSymbol(g_es_mixed_table, mixed.data(), sizeof(float4) * kEsTableN));
+    AT_CUDA_TRY(cudaMemcpyToSymbol(g_es_water_table, water.data(), sizeof(float4) * kEsTableN));
+    ready.push_back(dev);
+    return AT_OK;
+}
+
+}  // namespace
+
 extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_segments,
                                   const at_epi_col_t* cols, int32_t n_out_cols,
                                   at_epilogue_t** out) {
@@ -937,6 +1004,10 @@ extern "C" int at_epilogue_create(const at_epi_segment_t* segments, int32_t n_se
     *out = nullptr;
     AT_REQUIRE(segments != nullptr && n_segments > 0 && cols != nullptr && n_out_cols > 0,
                "at_epilogue_create: empty program");
+    {
+        const int rc = ensure_es_tables();
+        if (rc != AT_OK) return rc;
+    }
     std::vector<EpiTile> tiles;
     int n_in_cols = 0;
     for (int s = 0; s < n_segments; ++s) {

@@ -745,7 +745,15 @@ def run_gpu(args):
     }
 
     gc.collect()
-    grib_leg = None if args.skip_grib else grib_e2e(w, matrix_path, n_local, max(1, min(2, e2e_steps)), rank, world, barrier, max_over_ranks)
+    grib_leg = None
+    if not args.skip_grib:
+        try:  # an extra leg: it must not take the headline line down with it
+            grib_leg = grib_e2e(w, matrix_path, n_local, max(1, min(2, e2e_steps)), rank, world, barrier, max_over_ranks)
+        except Exception as e:  # noqa: BLE001
+            if world > 1:
+                raise  # the other ranks are inside its barriers
+            log("e2e_grib leg failed:", repr(e))
+            grib_leg = {"error": repr(e)}
 
     pipe4 = None
     if world == 1 and not args.skip_pipeline:

@@ -188,3 +188,61 @@ def test_float32_decode_feeds_the_fused_pipeline(cuda, tmp_path):
     finally:
         grib.set_decode_dtype(None)
     assert sum(f.decodes for f in fields) == 0
+
+
+def test_pointwise_filters_take_grib_fields_without_a_host_decode(cuda):
+    """uv_to_ddff and clip straight on GRIB-backed fields: values are decoded on the device
+    (float64, like to_numpy()) and the result equals the same filter on the host-decoded fields."""
+    from anemoi_transform_b200 import ekd
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    n = 40320
+    rng = np.random.default_rng(21)
+    lat, lon = syn.octahedral(96)
+    msgs, md = [], []
+    for lev in (500, 850):
+        for param in ("u", "v"):
+            msgs.append(ogrib.encode_grib2(rng.normal(0.0, 8.0, n), 16, 0))
+            md.append(dict(param=param, levelist=lev, step=0))
+    g_fields = [GribMessageField(m, n, d, latitudes=lat, longitudes=lon) for m, d in zip(msgs, md)]
+    a_fields = [ekd.ArrayField(ogrib.decode(m), d, latitudes=lat, longitudes=lon) for m, d in zip(msgs, md)]
+    for name, kw in (("uv_to_ddff", {}), ("clip_fields", dict(param="u", minimum=-3.0, maximum=4.0))):
+        got = F(name, **kw).forward(ekd.SimpleFieldList(g_fields))
+        assert sum(f.decodes for f in g_fields) == 0  # the filter itself decoded nothing on the host
+        want = F(name, **kw).forward(ekd.SimpleFieldList(a_fields))
+        assert [f.metadata("param") for f in got] == [f.metadata("param") for f in want]
+        for a, b in zip(got, want):
+            if a in g_fields:  # passed through untouched (clip of "u" leaves "v" alone): still the GRIB field
+                continue
+            assert a.to_numpy().dtype == b.to_numpy().dtype == np.float64
+            assert_same_values(a.to_numpy(), b.to_numpy(), name)
+    assert sum(f.decodes for f in g_fields) == 0
+
+
+def test_mixed_fieldlist_splits_between_device_and_host_decode(cuda, tmp_path):
+    """GRIB fields the device decodes, a GRIB field with a bitmap (missing values -> NaN, decoded
+    by the field itself) and a plain numpy field in one FieldList: each takes its own route, the
+    outputs keep the input order and equal scipy on the host-decoded values."""
+    from anemoi_transform_b200 import ekd
+    from anemoi_transform_b200.filters import create_filter_by_name as F
+
+    t_lat, t_lon = syn.octahedral(48)
+    d, i, p, shape = syn.bilinear_matrix(2.0, t_lat, t_lon)
+    s_lat, s_lon = syn.regular_latlon(2.0)
+    path = str(tmp_path / "m.npz")
+    syn.save_regrid_npz(path, d, i, p, shape, s_lat, s_lon, t_lat, t_lon)
+    m = csr_array((d, i, p), shape=shape)
+    n_src = shape[1]
+    rng = np.random.default_rng(31)
+    msgs = _messages(6, n_src, [16, 12], [0], [2, 1], seed=31)
+    fields = _fields(msgs, n_src, s_lat, s_lon)
+    bm = rng.uniform(size=n_src) > 0.2
+    with_bitmap = GribMessageField(ogrib.encode_grib2(rng.normal(285.0, 5.0, int(bm.sum())), 16, 0, bm), n_src, dict(param="sst", step=0), latitudes=s_lat, longitudes=s_lon)
+    plain = ekd.ArrayField(rng.normal(0.0, 1.0, n_src).astype(np.float32), dict(param="z", step=0), latitudes=s_lat, longitudes=s_lon)
+    mixed = fields[:3] + [with_bitmap] + fields[3:] + [plain]
+    out = F("regrid", matrix=path).forward(ekd.SimpleFieldList(mixed))
+    assert [f.metadata("param") for f in out] == ["t"] * 3 + ["sst"] + ["t"] * 3 + ["z"]
+    for f_in, f_out in zip(mixed, out):
+        host = f_in.to_numpy() if not isinstance(f_in, GribMessageField) else ogrib.decode(f_in.message(), n_points=n_src)
+        assert_same_values(f_out.to_numpy(), m @ host, str(f_in.metadata("param")))
+    assert sum(f.decodes for f in fields) == 0 and with_bitmap.decodes >= 1

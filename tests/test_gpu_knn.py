@@ -35,6 +35,11 @@ def _check_knn(cuda, src_xyz, tgt_xyz, k, ub=np.inf):
         diff = src[idx[q][idx[q] < src.shape[0]]] - tgt[q]
         d2 = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
         assert np.array_equal(np.sqrt(d2), dist[q][idx[q] < src.shape[0]])
+    if k == 1:
+        # without the tie flags k = 1 runs one thread per query (knn1_thread_kernel, leftovers
+        # through the list to the warp kernel): the same answer, bit for bit
+        i1, d1, _ = KnnIndex(src_xyz).query(tgt_xyz, k=1, distance_upper_bound=ub)
+        assert np.array_equal(i1.cpu().numpy(), idx) and np.array_equal(d1.cpu().numpy().view(np.uint64), dist.view(np.uint64))
     return idx, dist, tie, differ
 
 
@@ -190,3 +195,31 @@ def test_random_point_clouds_against_ckdtree(cuda, seed):
     k = int(min(rng.choice([1, 2, 5, 16]), max(1, n_s)))
     ub = np.inf if seed % 3 else float(np.median(cKDTree(src).query(tgt, k=1)[0])) or np.inf
     _check_knn(cuda, tuple(np.ascontiguousarray(src[:, j]) for j in range(3)), tuple(np.ascontiguousarray(tgt[:, j]) for j in range(3)), k, ub)
+
+
+def test_thread_per_query_kernel_on_crowded_duplicated_and_far_sources(cuda):
+    """k = 1 without tie flags (one thread per query): crowded polar rings and the 360 coincident
+    points of each pole of a regular lat-lon grid, queries sitting exactly on sources, queries
+    far outside a regional source set, an upper bound, NaN coordinates — against cKDTree and
+    against the warp-per-query kernel."""
+    from anemoi_transform_b200.device import KnnIndex
+
+    rng = np.random.default_rng(8)
+    src = _xyz(syn.regular_latlon(1.0))
+    # queries: the poles themselves, points within a degree of them, every source point, a global grid
+    lat = np.concatenate([[90.0, -90.0], 90.0 - rng.uniform(0, 1.5, 400), -90.0 + rng.uniform(0, 1.5, 400), syn.regular_latlon(1.0)[0][::7]])
+    lon = np.concatenate([[0.0, 123.0], rng.uniform(0, 360, 800), syn.regular_latlon(1.0)[1][::7]])
+    tgt = _xyz((lat, lon))
+    idx, dist, tie, _ = _check_knn(cuda, src, tgt, 1)
+    # a source exactly under the query: distance 0 (the other 359 points of that pole are 1e-16 away)
+    assert idx[0, 0] == 0 and dist[0, 0] == 0.0
+    n = src[0].size
+    assert idx[1, 0] == n - 360 + 123 and dist[1, 0] == 0.0
+    _check_knn(cuda, src, _xyz(syn.octahedral(40)), 1, ub=0.004)  # many queries find nothing within the bound
+    # regional sources, global queries: the tree search finishes what list and warp kernel hand on
+    lam = _xyz(syn.rotated_lam(50, 70, 0.03))
+    _check_knn(cuda, lam, _xyz(syn.octahedral(24)), 1)
+    # NaN query coordinates: no neighbour, padded like cKDTree pads misses
+    q = (np.array([np.nan, 1.0]), np.array([0.0, 0.0]), np.array([0.0, 0.0]))
+    i, d, _ = KnnIndex(lam).query(q, k=1)
+    assert int(i[0, 0]) == lam[0].size and np.isinf(float(d[0, 0])) and int(i[1, 0]) < lam[0].size
