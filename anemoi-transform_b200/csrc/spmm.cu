@@ -932,7 +932,7 @@ extern "C" int at_spmm(const at_csr_t* csr, const void* X, int x_dtype, int64_t 
 }
 
 // ---- epilogue handle --------------------------------------------------------------------
-// The cubic tables of es(T) (epilogue.cuh): float64 formulas sampled at four Chebyshev points of
+// The cubic table of es(T) (epilogue.cuh): the float64 formula sampled at four Chebyshev points of
 // every 0.5 K interval, interpolating cubic in f = (t - node) / 0.5, rounded to float32.  Once per
 // device and process.
 namespace {
@@ -947,8 +947,6 @@ double es_mixed_f64(double t) {
     const double a = (t - 250.16) / 23.0;
     return a * a * es_w + (1.0 - a * a) * es_i;
 }
-
-double es_water_f64(double t) { return 611.21 * std::exp(17.502 * (t - 273.16) / (t - 32.19)); }
 
 void fit_es_table(double (*fn)(double), float4* out) {
     const double pi = 3.14159265358979323846;
@@ -986,11 +984,9 @@ int ensure_es_tables() {
     AT_CUDA_TRY(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(mu);
     if (std::find(ready.begin(), ready.end(), dev) != ready.end()) return AT_OK;
-    std::vector<float4> mixed(kEsTableN), water(kEsTableN);
+    std::vector<float4> mixed(kEsTableN);
     fit_es_table(es_mixed_f64, mixed.data());
-    fit_es_table(es_water_f64, water.data());
     AT_CUDA_TRY(cudaMemcpyToSymbol(g_es_mixed_table, mixed.data(), sizeof(float4) * kEsTableN));
-    AT_CUDA_TRY(cudaMemcpyToSymbol(g_es_water_table, water.data(), sizeof(float4) * kEsTableN));
     ready.push_back(dev);
     return AT_OK;
 }
