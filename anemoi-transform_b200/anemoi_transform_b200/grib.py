@@ -4,7 +4,7 @@ In the reference a GRIB FieldList reaches a filter as earthkit-data `GribField`s
 `field.to_numpy(flatten=True)` (`filters/fields/regrid.py:309`, `matching.py:242-246`) has
 ecCodes decode one message to float64 on one core.  A field whose *class* provides
 `message()` (earthkit-data's `GribField.message()` returns the encoded message) and whose
-message is grid-point simple packing without a bitmap is uploaded packed — 2 bytes per point
+message is grid-point simple packing (with or without a bitmap) is uploaded packed — 2 bytes per point
 at 16 bits instead of 8 — and decoded by `grib_unpack_kernel` straight into the
 [points x fields] batch (`csrc/grib.cu`).  Everything else keeps the `to_numpy()` route.
 
@@ -97,12 +97,18 @@ class PackedFields:
 
     @property
     def packed_bytes(self) -> int:
-        return int(sum((self.n_points * i.bits_per_value + 7) // 8 for i in self.infos))
+        """Octets that cross PCIe: packed values, plus one bit per point for fields with a bitmap."""
+        total = 0
+        for i in self.infos:
+            values = i.n_values if (i.has_bitmap and i.n_values >= 0) else self.n_points
+            total += (values * i.bits_per_value + 7) // 8 + ((self.n_points + 7) // 8 if i.has_bitmap else 0)
+        return int(total)
 
 
 def packed_of(fields: Sequence[Any]) -> PackedFields | None:
-    """`PackedFields` when *every* field is a simple-packed GRIB message of the same grid size
-    without a bitmap, else None (the caller then uses `to_numpy()` for all of them)."""
+    """`PackedFields` when *every* field is a simple-packed GRIB message of the same grid size,
+    else None (the caller then uses `to_numpy()` for all of them).  Points a bitmap marks as
+    missing decode to NaN."""
     if not fields or not enabled():
         return None
     n = len(fields)
@@ -121,18 +127,24 @@ def packed_of(fields: Sequence[Any]) -> PackedFields | None:
         return None
     n_points = -1
     for f, info in zip(fields, infos):
+        # grid points of the field: with a bitmap the message says (n_points), the packed stream
+        # then holds only the n_values points that are present (the device decodes the rest to NaN)
         if info.has_bitmap:
-            return None
-        count = info.n_values if info.n_values >= 0 else info.n_points
+            count, packed_values = info.n_points, info.n_values
+        else:
+            count = info.n_values if info.n_values >= 0 else info.n_points
+            packed_values = count
         shape = getattr(f, "shape", None)
         if shape is not None:
             declared = math.prod(shape)
             if count >= 0 and count != declared:
                 return None
             count = declared
+            if not info.has_bitmap:
+                packed_values = count
         if count < 0 or (n_points >= 0 and count != n_points):
             return None
-        if info.data_length < (count * info.bits_per_value + 7) // 8:
+        if packed_values > count or (packed_values >= 0 and info.data_length < (packed_values * info.bits_per_value + 7) // 8):
             return None
         n_points = count
     return PackedFields(buffers, infos, n_points, pointers)
@@ -140,7 +152,7 @@ def packed_of(fields: Sequence[Any]) -> PackedFields | None:
 
 def split(fields: Sequence[Any]) -> tuple[PackedFields | None, list[int], list[int]]:
     """Partition a FieldList: (the messages the device decodes, their positions, the positions of
-    the fields that keep the `to_numpy()` route — other packings, bitmaps, wrappers, numpy fields)."""
+    the fields that keep the `to_numpy()` route — other packings, wrappers, numpy fields)."""
     if not fields or not enabled():
         return None, [], list(range(len(fields)))
     candidates = [i for i, f in enumerate(fields) if _message_of(f) is not None]
@@ -149,8 +161,7 @@ def split(fields: Sequence[Any]) -> tuple[PackedFields | None, list[int], list[i
     whole = packed_of(fields) if len(candidates) == len(fields) else None
     if whole is not None:
         return whole, list(range(len(fields))), []
-    # field by field: keep those that scan as simple packing without a bitmap and share the size
-    # of the first such field
+    # field by field: keep those that scan as simple packing and share the size of the first such field
     keep: list[int] = []
     n_points = -1
     for i in candidates:

@@ -7,8 +7,8 @@
 // at 16 bits, instead of 8 bytes of decoded float64) cross PCIe and the kernel below unpacks
 // them into columns of the [points x fields] batch the SpMM reads.
 //
-//   at_grib_scan      host: locate packing parameters and the packed values of one message
-//                     (editions 1 and 2, grid-point simple packing)
+//   at_grib_scan      host: locate packing parameters, the packed values and the bitmap of one
+//                     message (editions 1 and 2, grid-point simple packing)
 //   at_grib_unpack    device: Y = ((X · 2^E) + R) · 10^-D for a batch of fields, fused with the
 //                     field-major -> point-major transposition
 //
@@ -261,10 +261,101 @@ __device__ __forceinline__ void unpack_group(const uint8_t* __restrict__ src, co
     }
 }
 
+// ---- bitmaps: points without a value ------------------------------------------------------
+// A field with a bitmap packs only the points whose bit is set; point p's value is number
+// rank(p) = (set bits before p) of the stream.  grib_bitmap_rank_kernel writes, per field and per
+// tile of 256 points, the rank of the tile's first point (one warp per field, 32 tiles per step,
+// warp scan with carry); the unpack kernel adds the set bits of the lanes before it inside the
+// tile.  A missing point decodes to NaN (what earthkit-data's to_numpy() hands to the filters).
+__global__ void __launch_bounds__(32)
+    grib_bitmap_rank_kernel(uint8_t* __restrict__ packed, const GribColumn* __restrict__ cols, long long n_points) {
+    const GribColumn c = cols[blockIdx.x];
+    if (c.bitmap_offset < 0) return;
+    const int lane = threadIdx.x;
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(packed + c.bitmap_offset);  // 256-byte aligned
+    uint32_t* rank = reinterpret_cast<uint32_t*>(packed + c.rank_offset);
+    const long long n_tiles = (n_points + kTilePoints - 1) / kTilePoints;
+    uint32_t carry = 0;
+    for (long long t0 = 0; t0 < n_tiles; t0 += 32) {
+        const long long t = t0 + lane;
+        uint32_t count = 0;
+        if (t < n_tiles) {
+            const long long first = t * kTilePoints;
+            const int valid = static_cast<int>(min(static_cast<long long>(kTilePoints), n_points - first));
+#pragma unroll
+            for (int w = 0; w < kTilePoints / 32; ++w) {
+                const int v = valid - 32 * w;  // points of this word that exist
+                if (v <= 0) break;
+                uint32_t word = words[t * (kTilePoints / 32) + w];
+                if (v < 32) {
+                    // point i of the word is bit 7 - i % 8 of octet i / 8; octet j is bits 8j .. 8j+7 of the little-endian word
+                    const int whole = v >> 3, rest = v & 7;
+                    uint32_t mask = whole >= 4 ? 0xffffffffu : ((1u << (8 * whole)) - 1u);
+                    if (rest != 0) mask |= ((0xffu << (8 - rest)) & 0xffu) << (8 * whole);
+                    word &= mask;
+                }
+                count += __popc(word);
+            }
+        }
+        uint32_t inc = count;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (t < n_tiles) rank[t] = carry + inc - count;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+}
+
+// Value number `index` of a stream of nbits-wide big-endian fields that starts at `values`.
+__device__ __forceinline__ uint32_t extract_bits(const uint8_t* __restrict__ values, long long index, int nbits) {
+    const long long bit = index * nbits;
+    const uint8_t* b = values + (bit >> 3);
+    const int shift = static_cast<int>(bit & 7);
+    // shift + nbits <= 39 bits: five octets (the regions carry 16 octets of slack)
+    unsigned long long acc = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) acc = (acc << 8) | __ldg(b + i);
+    const uint32_t mask = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+    return static_cast<uint32_t>(acc >> (40 - shift - nbits)) & mask;
+}
+
+template <typename TOut>
+__device__ __forceinline__ void unpack_group_bitmap(const uint8_t* __restrict__ packed, const GribColumn& c, long long p0,
+                                                    long long n_points, int lane, int avail, TOut* __restrict__ dst) {
+    // this lane's octet of the bitmap: points p0 + 8·lane .. + 7, MSB first
+    uint32_t bits = 0;
+    if (avail > 0) {
+        bits = __ldg(packed + c.bitmap_offset + ((p0 >> 3) + lane));
+        if (avail < 8) bits &= (0xffu << (8 - avail)) & 0xffu;
+    }
+    uint32_t inc = __popc(bits);
+    const uint32_t mine = inc;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    const uint32_t* rank = reinterpret_cast<const uint32_t*>(packed + c.rank_offset);
+    long long index = static_cast<long long>(__ldg(rank + p0 / kTilePoints)) + (inc - mine);
+    const uint8_t* values = packed + c.byte_offset;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k >= avail) break;
+        if (bits & (0x80u >> k)) {
+            const uint32_t x = c.nbits == 0 ? 0u : extract_bits(values, index, c.nbits);
+            ++index;
+            const double y = c.nbits == 0 ? c.reference : __dmul_rn(__dadd_rn(__dmul_rn(static_cast<double>(x), c.binary), c.reference), c.decimal);
+            dst[k] = static_cast<TOut>(y);
+        } else {
+            dst[k] = static_cast<TOut>(__longlong_as_double(0x7ff8000000000000ll));
+        }
+    }
+}
+
 // One CTA per (tile of 256 points, group of 32 fields).  Warp w unpacks fields w, w+8, w+16,
 // w+24 of the group (every lane 8 consecutive points: coalesced reads of nbits octets per lane)
 // into shared memory; then every warp writes rows of 32 adjacent columns of the batch.
-template <typename TOut>
+template <typename TOut, bool BITMAPS>
 __global__ void __launch_bounds__(256)
     grib_unpack_kernel(const uint8_t* __restrict__ packed, const GribColumn* __restrict__ cols, int n_fields, long long n_points,
                        TOut* __restrict__ out, long long ld, unsigned n_field_groups) {
@@ -277,15 +368,19 @@ __global__ void __launch_bounds__(256)
     const long long p0 = static_cast<long long>(blockIdx.x / n_field_groups) * kTilePoints;
     const int f0 = static_cast<int>(blockIdx.x % n_field_groups) * kTileFields;
     const long long p = p0 + lane * 8;
-    const int avail = static_cast<int>(min(8ll, n_points - p));
+    const int avail = static_cast<int>(max(0ll, min(8ll, n_points - p)));
 #pragma unroll 1
     for (int j = warp; j < kTileFields; j += 8) {
         const int f = f0 + j;
-        if (f >= n_fields || avail <= 0) continue;
+        if (f >= n_fields) continue;  // warp-uniform
         const GribColumn c = cols[f];
-        const uint8_t* src = packed + c.byte_offset + (p >> 3) * c.nbits;
         TOut v[8];
-        unpack_group<TOut>(src, c, avail, v);
+        if (BITMAPS && c.bitmap_offset >= 0) {  // warp-uniform: the whole warp takes part in the scan
+            unpack_group_bitmap<TOut>(packed, c, p0, n_points, lane, avail, v);
+        } else {
+            if (avail <= 0) continue;
+            unpack_group<TOut>(packed + c.byte_offset + (p >> 3) * c.nbits, c, avail, v);
+        }
         // point 8·lane + k of the tile is kept at position 32·k + lane: consecutive lanes write
         // consecutive words (position 8·lane + k put 32 lanes on 2 banks: ncu counted 121 M
         // bank conflicts per launch and the kernel sat at 0.52 of the HBM peak)
@@ -300,37 +395,73 @@ __global__ void __launch_bounds__(256)
         for (int r = warp; r < rows; r += 8) out[(p0 + r) * ld + f] = tile[lane * kPitch + (r & 7) * 32 + (r >> 3)];
 }
 
-int grib_unpack_launch(const uint8_t* d_packed, const GribColumn* d_cols, int n_fields, int64_t n_points, int out_dtype, void* d_pm,
-                       int64_t ld, cudaStream_t st) {
+template <typename TOut, bool BITMAPS>
+static int launch_unpack(const uint8_t* d_packed, const GribColumn* d_cols, int n_fields, int64_t n_points, TOut* out, int64_t ld,
+                         unsigned grid, unsigned n_field_groups, cudaStream_t st) {
+    const size_t smem = sizeof(TOut) * kTileFields * (kTilePoints + 1);
+    if (smem > 48 * 1024) {  // above the default: opt in (idempotent)
+        AT_CUDA_TRY(cudaFuncSetAttribute(grib_unpack_kernel<TOut, BITMAPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    }
+    grib_unpack_kernel<TOut, BITMAPS><<<grid, 256, smem, st>>>(d_packed, d_cols, n_fields, n_points, out, ld, n_field_groups);
+    AT_LAUNCH_CHECK("grib_unpack_kernel");
+    return AT_OK;
+}
+
+int grib_unpack_launch(uint8_t* d_packed, const GribColumn* d_cols, int n_fields, int64_t n_points, int out_dtype, void* d_pm,
+                       int64_t ld, bool any_bitmap, cudaStream_t st) {
     if (n_fields == 0 || n_points == 0) return AT_OK;
     const unsigned n_field_groups = static_cast<unsigned>((n_fields + kTileFields - 1) / kTileFields);
     const long long blocks = ((n_points + kTilePoints - 1) / kTilePoints) * n_field_groups;
     if (blocks >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "GRIB unpack: batch too large for one launch");
     const unsigned grid = static_cast<unsigned>(blocks);
-    if (out_dtype == AT_F32) {
-        const size_t smem = sizeof(float) * kTileFields * (kTilePoints + 1);
-        grib_unpack_kernel<float><<<grid, 256, smem, st>>>(d_packed, d_cols, n_fields, n_points, static_cast<float*>(d_pm), ld, n_field_groups);
-    } else {
-        const size_t smem = sizeof(double) * kTileFields * (kTilePoints + 1);
-        static bool raised = false;  // above the 48 KB default: opt in once per process (per device is implied by the attribute cache)
-        if (!raised) {
-            AT_CUDA_TRY(cudaFuncSetAttribute(grib_unpack_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            raised = true;
-        }
-        grib_unpack_kernel<double><<<grid, 256, smem, st>>>(d_packed, d_cols, n_fields, n_points, static_cast<double*>(d_pm), ld, n_field_groups);
+    if (any_bitmap) {
+        grib_bitmap_rank_kernel<<<static_cast<unsigned>(n_fields), 32, 0, st>>>(d_packed, d_cols, n_points);
+        AT_LAUNCH_CHECK("grib_bitmap_rank_kernel");
+        if (out_dtype == AT_F32) return launch_unpack<float, true>(d_packed, d_cols, n_fields, n_points, static_cast<float*>(d_pm), ld, grid, n_field_groups, st);
+        return launch_unpack<double, true>(d_packed, d_cols, n_fields, n_points, static_cast<double*>(d_pm), ld, grid, n_field_groups, st);
     }
-    AT_LAUNCH_CHECK("grib_unpack_kernel");
-    return AT_OK;
+    if (out_dtype == AT_F32) return launch_unpack<float, false>(d_packed, d_cols, n_fields, n_points, static_cast<float*>(d_pm), ld, grid, n_field_groups, st);
+    return launch_unpack<double, false>(d_packed, d_cols, n_fields, n_points, static_cast<double*>(d_pm), ld, grid, n_field_groups, st);
+}
+
+static size_t round_up_256(size_t n) { return (n + 255) / 256 * 256; }
+
+GribFootprint grib_footprint(const at_grib_field_t& info, int64_t n_points) {
+    GribFootprint fp;
+    const int64_t n_values = info.has_bitmap ? (info.n_values >= 0 ? info.n_values : n_points) : n_points;
+    int64_t octets = (n_values * std::max(info.bits_per_value, 0) + 7) / 8;
+    if (info.has_bitmap && info.n_values < 0) octets = std::max<int64_t>(info.data_length, 0);  // count unknown: the whole section
+    fp.value_octets = static_cast<size_t>(std::min<int64_t>(octets, std::max<int64_t>(info.data_length, 0)));
+    fp.values = round_up_256(fp.value_octets + 16);
+    if (info.has_bitmap) {
+        fp.bitmap_octets = static_cast<size_t>((n_points + 7) / 8);
+        fp.bitmap = round_up_256(fp.bitmap_octets + 32);
+        fp.ranks = round_up_256(static_cast<size_t>((n_points + kTilePoints - 1) / kTilePoints + 1) * sizeof(uint32_t));
+    }
+    return fp;
 }
 
 int grib_column_of(const at_grib_field_t& info, int64_t n_points, int64_t byte_offset, GribColumn* out) {
-    AT_REQUIRE(info.has_bitmap == 0, "GRIB unpack: messages with a bitmap are decoded by the caller (to_numpy), not here");
     AT_REQUIRE(info.bits_per_value >= 0 && info.bits_per_value <= 32, "GRIB unpack: bitsPerValue %d out of range", info.bits_per_value);
-    AT_REQUIRE(info.n_values < 0 || info.n_values == n_points, "GRIB unpack: message holds %lld values, the batch has %lld points",
-               (long long)info.n_values, (long long)n_points);
-    const int64_t need = (n_points * info.bits_per_value + 7) / 8;
-    AT_REQUIRE(info.data_length >= need, "GRIB unpack: %lld octets of packed values, %lld needed", (long long)info.data_length, (long long)need);
+    const GribFootprint fp = grib_footprint(info, n_points);
+    if (info.has_bitmap) {
+        AT_REQUIRE(info.n_points < 0 || info.n_points == n_points, "GRIB unpack: the bitmap covers %lld points, the batch has %lld",
+                   (long long)info.n_points, (long long)n_points);
+        AT_REQUIRE(info.n_values <= n_points, "GRIB unpack: %lld values for %lld points", (long long)info.n_values, (long long)n_points);
+        AT_REQUIRE(info.bitmap_offset >= 0 && info.bitmap_offset + static_cast<int64_t>(fp.bitmap_octets) <= info.message_length,
+                   "GRIB unpack: the bitmap runs past the end of the message");
+        if (info.n_values >= 0)
+            AT_REQUIRE(info.data_length >= (info.n_values * info.bits_per_value + 7) / 8, "GRIB unpack: %lld octets of packed values, %lld needed",
+                       (long long)info.data_length, (long long)((info.n_values * info.bits_per_value + 7) / 8));
+    } else {
+        AT_REQUIRE(info.n_values < 0 || info.n_values == n_points, "GRIB unpack: message holds %lld values, the batch has %lld points",
+                   (long long)info.n_values, (long long)n_points);
+        const int64_t need = (n_points * info.bits_per_value + 7) / 8;
+        AT_REQUIRE(info.data_length >= need, "GRIB unpack: %lld octets of packed values, %lld needed", (long long)info.data_length, (long long)need);
+    }
     out->byte_offset = byte_offset;
+    out->bitmap_offset = info.has_bitmap ? byte_offset + static_cast<int64_t>(fp.values) : -1;
+    out->rank_offset = info.has_bitmap ? byte_offset + static_cast<int64_t>(fp.values + fp.bitmap) : -1;
     out->reference = info.reference_value;
     out->binary = repeated_power(info.binary_scale, 2);
     out->decimal = repeated_power(-info.decimal_scale, 10);
@@ -374,6 +505,7 @@ extern "C" int at_grib_unpack(const void* d_packed, const int64_t* byte_offsets,
     std::vector<GribColumn> cols(static_cast<size_t>(n_fields));
     for (int64_t f = 0; f < n_fields; ++f) {
         AT_REQUIRE(byte_offsets[f] >= 0, "at_grib_unpack: negative offset");
+        AT_REQUIRE(fields[f].has_bitmap == 0, "at_grib_unpack: messages with a bitmap go through at_hostio_upload_grib / at_hostio_regrid_grib (they stage the bitmap too)");
         const int rc = grib_column_of(fields[f], n_points, byte_offsets[f], &cols[static_cast<size_t>(f)]);
         if (rc != AT_OK) return rc;
     }
@@ -384,7 +516,8 @@ extern "C" int at_grib_unpack(const void* d_packed, const int64_t* byte_offsets,
     int rc = AT_OK;
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);  // `cols` is pageable and leaves scope
     if (e != cudaSuccess) rc = set_error(AT_ERR_CUDA, "at_grib_unpack: %s", cudaGetErrorString(e));
-    if (rc == AT_OK) rc = grib_unpack_launch(static_cast<const uint8_t*>(d_packed), d_cols, static_cast<int>(n_fields), n_points, out_dtype, d_pm, ld, st);
+    if (rc == AT_OK)
+        rc = grib_unpack_launch(const_cast<uint8_t*>(static_cast<const uint8_t*>(d_packed)), d_cols, static_cast<int>(n_fields), n_points, out_dtype, d_pm, ld, false, st);
     device_free(d_cols);  // waits for the device, like cudaFree
     return rc;
 }

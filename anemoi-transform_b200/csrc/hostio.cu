@@ -481,10 +481,11 @@ int upload_chunk(at_hostio* io, const void* const* fields, const uint8_t* pinned
 // table of kernel parameters, and grib_unpack_kernel takes the place of the pack transposition.
 size_t grib_table_bytes(int nf) { return round_up(static_cast<size_t>(nf) * sizeof(GribColumn), 4096); }
 
-size_t grib_chunk_bytes(const at_grib_field_t* infos, int nf) {
-    size_t bytes = grib_table_bytes(nf);
-    for (int f = 0; f < nf; ++f) bytes += round_up(static_cast<size_t>(std::max<int64_t>(infos[f].data_length, 0)) + 16, kAlign);
-    return bytes;
+// Largest footprint of a field in a chunk buffer (+ its share of the parameter table).
+size_t grib_packed_stride(const at_grib_field_t* infos, int64_t n_fields, int64_t n_points) {
+    size_t stride = 0;
+    for (int64_t f = 0; f < n_fields; ++f) stride = std::max(stride, grib_footprint(infos[f], n_points).total() + sizeof(GribColumn));
+    return stride;
 }
 
 int upload_chunk_grib(at_hostio* io, const void* const* messages, const at_grib_field_t* infos, int nf, int64_t n_points,
@@ -495,20 +496,25 @@ int upload_chunk_grib(at_hostio* io, const void* const* messages, const at_grib_
     char* const d = io->d_in[slot];
     GribColumn* table = reinterpret_cast<GribColumn*>(h);
     struct Task {
-        int f;
-        size_t off, len;
+        const char* src;
+        size_t at, len;
     };
     std::vector<Task> tasks;
-    std::vector<size_t> base(static_cast<size_t>(nf));
     size_t cursor = grib_table_bytes(nf);
+    bool any_bitmap = false;
     for (int f = 0; f < nf; ++f) {
-        base[static_cast<size_t>(f)] = cursor;
         const int rc = grib_column_of(infos[f], n_points, static_cast<int64_t>(cursor), &table[f]);
         if (rc != AT_OK) return rc;
-        // what the kernel reads: the packed values of n_points points (the section may be padded)
-        const size_t len = static_cast<size_t>((n_points * infos[f].bits_per_value + 7) / 8);
-        for (size_t o = 0; o < len; o += kPiece) tasks.push_back({f, o, std::min(kPiece, len - o)});
-        cursor += round_up(len + 16, kAlign);
+        const GribFootprint fp = grib_footprint(infos[f], n_points);
+        // what the kernel reads: the packed values (the section may be padded), and the bitmap
+        const char* msg = static_cast<const char*>(messages[f]);
+        for (size_t o = 0; o < fp.value_octets; o += kPiece) tasks.push_back({msg + infos[f].data_offset + o, cursor + o, std::min(kPiece, fp.value_octets - o)});
+        if (infos[f].has_bitmap) {
+            any_bitmap = true;
+            for (size_t o = 0; o < fp.bitmap_octets; o += kPiece)
+                tasks.push_back({msg + infos[f].bitmap_offset + o, cursor + fp.values + o, std::min(kPiece, fp.bitmap_octets - o)});
+        }
+        cursor += fp.total();
     }
     if (cursor > io->in_slot_bytes) return set_error(AT_ERR_INVALID, "hostio grib upload: chunk of %zu bytes exceeds the slot (%zu)", cursor, io->in_slot_bytes);
     cudaStream_t s_in = io->s_in;
@@ -516,17 +522,15 @@ int upload_chunk_grib(at_hostio* io, const void* const* messages, const at_grib_
     std::atomic<int> err{static_cast<int>(cudaSuccess)};
     io->workers->parallel_for(static_cast<int64_t>(tasks.size()), [&](int64_t i) {
         const Task& t = tasks[static_cast<size_t>(i)];
-        const char* src = static_cast<const char*>(messages[t.f]) + infos[t.f].data_offset + t.off;
-        const size_t at = base[static_cast<size_t>(t.f)] + t.off;
-        copy_streaming(h + at, src, t.len);
-        const cudaError_t e = cudaMemcpyAsync(d + at, h + at, t.len, cudaMemcpyHostToDevice, s_in);
+        copy_streaming(h + t.at, t.src, t.len);
+        const cudaError_t e = cudaMemcpyAsync(d + t.at, h + t.at, t.len, cudaMemcpyHostToDevice, s_in);
         if (e != cudaSuccess) err.store(static_cast<int>(e));
     });
     if (err.load() != static_cast<int>(cudaSuccess))
         return set_error(AT_ERR_CUDA, "hostio grib upload: %s", cudaGetErrorString(static_cast<cudaError_t>(err.load())));
     AT_CUDA_TRY(cudaEventRecord(io->h2d_done[slot], s_in));
     AT_CUDA_TRY(cudaStreamWaitEvent(st, io->h2d_done[slot], 0));
-    const int rc = grib_unpack_launch(reinterpret_cast<const uint8_t*>(d), reinterpret_cast<const GribColumn*>(d), nf, n_points, x_dtype, d_pm, ld, st);
+    const int rc = grib_unpack_launch(reinterpret_cast<uint8_t*>(d), reinterpret_cast<const GribColumn*>(d), nf, n_points, x_dtype, d_pm, ld, any_bitmap, st);
     if (rc != AT_OK) return rc;
     AT_CUDA_TRY(cudaEventRecord(io->in_free[slot], st));
     return AT_OK;
@@ -831,10 +835,8 @@ static int regrid_impl(at_hostio_t* io, int op, const at_csr_t* csr, const int64
     const int xe = x_dtype == AT_F32 ? 4 : 8, ye = y_dtype == AT_F32 ? 4 : 8;
     const size_t in_fb = static_cast<size_t>(n_src) * xe, in_stride = round_up(std::max<size_t>(in_fb, 1), kAlign);
     const size_t out_fb = static_cast<size_t>(n_tgt) * ye, out_stride = round_up(std::max<size_t>(out_fb, 1), kAlign);
-    size_t packed_stride = 0;  // largest packed field (+ its share of the parameter table)
-    if (grib != nullptr)
-        for (int64_t f = 0; f < n_fields; ++f)
-            packed_stride = std::max(packed_stride, round_up(static_cast<size_t>(std::max<int64_t>(grib[f].data_length, 0)) + 16, kAlign) + sizeof(GribColumn));
+    // largest packed field (+ its share of the parameter table)
+    const size_t packed_stride = grib != nullptr ? grib_packed_stride(grib, n_fields, n_src) : 0;
     // a chunk is bounded by the slots (what crosses PCIe) and by its decoded [points x fields] batch
     const size_t bound_stride = grib != nullptr ? std::max({packed_stride, out_stride, in_stride / 4}) : std::max(in_stride, out_stride);
     const int64_t chunk = chunk_fields(n_fields, bound_stride, 4);
@@ -922,9 +924,7 @@ extern "C" int at_hostio_upload_grib(at_hostio_t* io, const void* const* message
     for (int64_t f = 0; f < n_fields; ++f) AT_REQUIRE(messages[f] != nullptr, "at_hostio_upload_grib: message %lld is null", (long long)f);
     std::lock_guard<std::mutex> lk(io->mu);
     DeviceGuard guard(io->device);
-    size_t packed_stride = 0;
-    for (int64_t f = 0; f < n_fields; ++f)
-        packed_stride = std::max(packed_stride, round_up(static_cast<size_t>(std::max<int64_t>(fields[f].data_length, 0)) + 16, kAlign) + sizeof(GribColumn));
+    const size_t packed_stride = grib_packed_stride(fields, n_fields, n_points);
     const int64_t chunk = chunk_fields(n_fields, packed_stride, 1);
     int rc = ensure_in_slots(io, static_cast<size_t>(chunk) * packed_stride + 8192, true);
     if (rc != AT_OK) return rc;

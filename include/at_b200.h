@@ -339,10 +339,10 @@ AT_API int at_hostio_regrid(at_hostio_t* io, int op, const at_csr_t* csr, const 
  * of float64) and decode them on the device:
  *     Y = ((X * 2^E) + R) * 10^-D        (WMO FM 92, regulation 92.9.4; float64, unfused)
  * Supported: editions 1 and 2, grid-point simple packing (BDS flag 0 / template 5.0),
- * 0..32 bits per value, ECMWF's long edition-1 messages.  Anything else (second-order, CCSDS,
- * JPEG, spectral, several fields per message) is AT_ERR_UNSUPPORTED from at_grib_scan and the
- * caller decodes such fields itself; messages with a bitmap scan fine (has_bitmap = 1) but are
- * refused by the unpack calls.
+ * 0..32 bits per value, ECMWF's long edition-1 messages, bitmaps (a point whose bit is clear
+ * decodes to NaN, which is what earthkit-data's to_numpy() hands to the filters).  Anything else
+ * (second-order, CCSDS, JPEG, spectral, several fields per message, predefined bitmaps) is
+ * AT_ERR_UNSUPPORTED from at_grib_scan and the caller decodes such fields itself.
  */
 typedef struct at_grib_field {
     int32_t edition;        /* 1 | 2 */
@@ -369,13 +369,16 @@ AT_API int at_grib_scan_many(const void* const* messages, const size_t* lengths,
  * device memory.  d_packed: device buffer; byte_offsets[f] (host): where field f's packed
  * values (message + data_offset) start inside it; fields (host): the scans.
  * out_dtype AT_F64 (what to_numpy gives) or AT_F32 (that value rounded to float32).
+ * Messages with a bitmap are refused here (the packed values alone do not say where they go):
+ * at_hostio_upload_grib / at_hostio_regrid_grib stage the bitmap as well.
  */
 AT_API int at_grib_unpack(const void* d_packed, const int64_t* byte_offsets, const at_grib_field_t* fields,
                    int64_t n_fields, int64_t n_points, int out_dtype, void* d_pm, int64_t ld, void* stream);
 /*
  * at_hostio_upload / at_hostio_regrid for packed fields: messages[f] is the host pointer to
- * message f (any memory), fields[f] its scan.  Only data_length octets per field are staged and
- * cross PCIe; the unpack kernel replaces the pack transposition.  x_dtype: the dtype the values
+ * message f (any memory), fields[f] its scan.  Only the packed values (and the bitmap, one bit
+ * per point, of a field that has one) are staged and cross PCIe; the unpack kernel replaces the
+ * pack transposition.  x_dtype: the dtype the values
  * are decoded to (the dtype of the [points x fields] batch the matrix is applied to).
  */
 AT_API int at_hostio_upload_grib(at_hostio_t* io, const void* const* messages, const at_grib_field_t* fields,

@@ -93,11 +93,37 @@ def test_raw_unpack_entry_point_validates(cuda):
         _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, infos, 5, n_points + 1, _cabi.AT_F64, _ptr(out), 8, stream_ptr())
     with pytest.raises(ValueError, match="leading dimension"):
         _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, infos, 5, n_points, _cabi.AT_F64, _ptr(out), 4, stream_ptr())
+    # packed values alone are not enough for a message with a bitmap: that goes through the engine
     bm = np.random.default_rng(0).uniform(size=n_points) > 0.5
     with_bitmap = ogrib.encode_grib2(np.arange(float(bm.sum())), 16, 0, bm)
     one = (_cabi.GribInfo * 1)(grib.scan(with_bitmap))
     with pytest.raises(ValueError, match="bitmap"):
         _cabi.call("at_grib_unpack", _ptr(d_blob), offsets, one, 1, n_points, _cabi.AT_F64, _ptr(out), 8, stream_ptr())
+
+
+@pytest.mark.parametrize("n_points", [5, 255, 256, 257, 1001, 40320])
+def test_bitmaps_decode_to_nan_where_the_bit_is_clear(cuda, n_points):
+    """Fields with a bitmap (editions 1 and 2, several widths, all-present / all-missing /
+    random / striped masks) next to fields without one: values at the set bits, NaN elsewhere."""
+    from anemoi_transform_b200 import grib
+
+    rng = np.random.default_rng(n_points)
+    masks = [rng.uniform(size=n_points) > 0.3, np.ones(n_points, bool), np.zeros(n_points, bool), np.arange(n_points) % 3 == 0, rng.uniform(size=n_points) > 0.97]
+    masks[2][n_points // 2] = True  # (an encoder needs at least one value)
+    msgs = []
+    for k, bm in enumerate(masks * 2):
+        nb = (16, 12, 24, 7, 32, 9, 8, 16, 11, 20)[k]
+        enc = ogrib.encode_grib2 if k % 2 == 0 else ogrib.encode_grib1
+        msgs.append(enc(rng.normal(285.0, 5.0, int(bm.sum())), nb, 0 if k % 3 else 1, bm))
+        msgs.append(enc(rng.normal(0.0, 8.0, n_points), nb, 0))  # and a field without a bitmap in between
+    want = np.stack([ogrib.decode(m, n_points=n_points) for m in msgs])
+    assert np.isnan(want).any()
+    packed = grib.packed_of(_fields(msgs, n_points))
+    assert packed is not None and packed.n_fields == len(msgs)
+    got = grib.upload(packed).data[:, : len(msgs)].cpu().numpy().T
+    assert_same_values(got, want, "bitmap decode float64")
+    got32 = grib.upload(packed, np.float32).data[:, : len(msgs)].cpu().numpy().T
+    assert_same_values(got32, want.astype(np.float32), "bitmap decode float32")
 
 
 @pytest.mark.parametrize("mdtype", [np.float32, np.float64])
@@ -220,9 +246,10 @@ def test_pointwise_filters_take_grib_fields_without_a_host_decode(cuda):
 
 
 def test_mixed_fieldlist_splits_between_device_and_host_decode(cuda, tmp_path):
-    """GRIB fields the device decodes, a GRIB field with a bitmap (missing values -> NaN, decoded
-    by the field itself) and a plain numpy field in one FieldList: each takes its own route, the
-    outputs keep the input order and equal scipy on the host-decoded values."""
+    """GRIB fields the device decodes (one of them with a bitmap: missing values -> NaN, which the
+    matrix spreads to the targets that use them), a wrapper field and a plain numpy field in one
+    FieldList: each takes its own route, the outputs keep the input order and equal scipy on the
+    host-decoded values."""
     from anemoi_transform_b200 import ekd
     from anemoi_transform_b200.filters import create_filter_by_name as F
 
@@ -239,10 +266,15 @@ def test_mixed_fieldlist_splits_between_device_and_host_decode(cuda, tmp_path):
     bm = rng.uniform(size=n_src) > 0.2
     with_bitmap = GribMessageField(ogrib.encode_grib2(rng.normal(285.0, 5.0, int(bm.sum())), 16, 0, bm), n_src, dict(param="sst", step=0), latitudes=s_lat, longitudes=s_lon)
     plain = ekd.ArrayField(rng.normal(0.0, 1.0, n_src).astype(np.float32), dict(param="z", step=0), latitudes=s_lat, longitudes=s_lon)
-    mixed = fields[:3] + [with_bitmap] + fields[3:] + [plain]
+    from anemoi_transform_b200.fields import new_field_from_numpy
+
+    doubled = rng.normal(1.0, 0.1, n_src)
+    wrapper = new_field_from_numpy(doubled, template=fields[0], param="t2")  # forwards message() of the field it wraps
+    mixed = fields[:3] + [with_bitmap, wrapper] + fields[3:] + [plain]
     out = F("regrid", matrix=path).forward(ekd.SimpleFieldList(mixed))
-    assert [f.metadata("param") for f in out] == ["t"] * 3 + ["sst"] + ["t"] * 3 + ["z"]
+    assert [f.metadata("param") for f in out] == ["t"] * 3 + ["sst", "t2"] + ["t"] * 3 + ["z"]
     for f_in, f_out in zip(mixed, out):
-        host = f_in.to_numpy() if not isinstance(f_in, GribMessageField) else ogrib.decode(f_in.message(), n_points=n_src)
+        host = ogrib.decode(f_in.message(), n_points=n_src) if isinstance(f_in, GribMessageField) else np.asarray(f_in.to_numpy()).reshape(-1)
         assert_same_values(f_out.to_numpy(), m @ host, str(f_in.metadata("param")))
-    assert sum(f.decodes for f in fields) == 0 and with_bitmap.decodes >= 1
+    assert np.isnan(out[3].to_numpy()).any() and not np.isnan(out[3].to_numpy()).all()
+    assert sum(f.decodes for f in fields) == 0 and with_bitmap.decodes == 0

@@ -144,12 +144,18 @@ def test_only_fields_that_own_a_message_take_the_packed_route(native_library):
     # a wrapper forwards message() to the field it wraps, whose data it replaced: not packed
     wrapped = new_field_from_numpy(v * 2, template=f)
     assert wrapped.message() == f.message() and grib.packed_of([wrapped]) is None
-    # bitmaps, mixed lists and grids of another size keep the to_numpy() route
+    # a bitmap is fine (missing points decode to NaN on the device) as long as it covers the grid
     bm = rng.uniform(size=500) > 0.5
     with_bitmap = GribMessageField(ogrib.encode_grib2(v[bm], 16, 0, bm), 500, {"param": "sst"})
-    assert grib.packed_of([with_bitmap]) is None
+    both = grib.packed_of([f, with_bitmap])
+    assert both is not None and both.n_points == 500 and both.packed_bytes == 1000 + 2 * int(bm.sum()) + 63
+    short_bitmap = GribMessageField(ogrib.encode_grib2(v[:400][bm[:400]], 16, 0, bm[:400]), 500, {"param": "sst"})
+    assert grib.packed_of([short_bitmap]) is None
+    # mixed sizes, other packings and plain numpy fields keep the to_numpy() route; split() sorts them out
     other = GribMessageField(ogrib.encode_grib2(v[:400], 16), 400, {"param": "t"})
     assert grib.packed_of([f, other]) is None
+    packed, packed_idx, rest = grib.split([f, wrapped, with_bitmap, other])
+    assert packed is not None and packed_idx == [0, 2] and rest == [1, 3]
     import os
 
     os.environ["AT_B200_GRIB_DEVICE_DECODE"] = "0"
