@@ -336,16 +336,54 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
 // Warp w of a CTA owns tile-table entry blockIdx.y * 8 + w (32 lanes x 4 input columns, one
 // kind) for all of the CTA's rows: the 8 warps together read 4 KB of contiguous columns per row
 // (DRAM page locality), and everything row-invariant (pressures, clip bounds, mask bits) lives
-// in registers.  Copy-like tiles (clip / mask, affine, impute) are latency-bound: kPwRows
-// rows of loads in flight.  Transcendental tiles are issue-bound (uv_to_ddff is ~85 instructions per pair against
-// ~88 issue slots per 16 bytes at the HBM roofline): one copy of the epilogue code, the next
-// row's load in flight behind it, 4 CTAs per SM.
+// in registers.  Both paths are bound by bytes in flight before anything else (HBM latency x
+// bandwidth is ~35 KB per SM): copy-like tiles (clip / mask, affine, impute) keep kPwRows rows
+// of loads in flight in registers; transcendental tiles, which have no registers to spare at the
+// 64-register cap (4 CTAs per SM), keep kPwAhead rows in flight in shared memory instead —
+// cp.async (LDGSTS) into a per-lane ring, 16 bytes per lane and row, read back by the lane that
+// copied them (no barrier, no bank conflict) — behind one copy of the epilogue code.
 constexpr int kPwRows = 4;
+constexpr int kPwCtaRows = 32;  // rows per CTA (launch_pointwise)
+#ifndef AT_PW_AHEAD
+#define AT_PW_AHEAD 4
+#endif
+constexpr int kPwAhead = AT_PW_AHEAD;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// a lane's 4 columns of one row: global -> its ring slot (asynchronously), ring slot -> registers
+__device__ __forceinline__ void ring_fetch(uint32_t slot, const float* p) { cp_async16(slot, p); }
+__device__ __forceinline__ void ring_fetch(uint32_t slot, const double* p) {
+    cp_async16(slot, p);
+    cp_async16(slot + 16, p + 2);
+}
+__device__ __forceinline__ void ring_read(uint32_t slot, float& a, float& b, float& c, float& d) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(slot) : "memory");
+}
+__device__ __forceinline__ void ring_read(uint32_t slot, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(slot) : "memory");
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c), "=d"(d) : "r"(slot + 16) : "memory");
+}
 
 template <typename T, uint32_t FAM>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_kernel(const PointwiseArgs<T> f) {
-    const long long r0 = static_cast<long long>(blockIdx.x) * f.rows_per_cta;
-    const int nrows = static_cast<int>(min(static_cast<long long>(f.rows_per_cta), f.n_rows - r0));
+    constexpr int kSlot = 4 * sizeof(T);  // bytes a lane owns per row
+    constexpr int kAhead = sizeof(T) == 4 ? kPwAhead : (kPwAhead < 4 ? kPwAhead : 4);  // float64: 2 CTAs per SM of twice the bytes
+    __shared__ __align__(16) unsigned char s_ring[kWarps * kAhead * kWarp * kSlot];
+    __shared__ uint8_t s_mask[kPwCtaRows];
+    const long long r0 = static_cast<long long>(blockIdx.x) * kPwCtaRows;
+    const int nrows = static_cast<int>(min(static_cast<long long>(kPwCtaRows), f.n_rows - r0));
+    // the CTA's slice of the row mask, once (before any warp leaves: every thread reaches the barrier)
+    if (f.row_mask != nullptr) {
+        if (threadIdx.x < nrows) s_mask[threadIdx.x] = f.row_mask[r0 + threadIdx.x];
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // A CTA covers up to 8 table entries; when fewer are left (narrow batches) the spare warps
     // take a share of the rows instead of idling: warp w -> entry w % t_here, row group w / t_here.
@@ -374,7 +412,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
                 masked[j] = false;
                 if (lr + j < nrows) {
                     load4(xcol + static_cast<size_t>(src_row(r0 + lr + j)) * f.ldx, a[j][0], a[j][1], a[j][2], a[j][3]);
-                    if (any_mask) masked[j] = f.row_mask[r0 + lr + j] != 0;
+                    if (any_mask) masked[j] = s_mask[lr + j] != 0;
                 }
             }
 #pragma unroll
@@ -388,36 +426,30 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
 
     const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
     if (group >= nrows) return;
-    // Transcendental kinds: one copy of the epilogue code, kAhead rows of loads in flight behind
-    // it (a rotating register queue).
-    constexpr int kAhead = 1;  // measured: 3 rows ahead spills at the 64-register cap and is slower (uv2ddff 0.88 -> 0.93 ms)
-    T q[kAhead][4];
-    bool qmask[kAhead];
+    // Transcendental kinds: one copy of the epilogue code behind a ring of kAhead rows in flight.
+    // Slot k of a lane is refilled only after the epilogue has consumed the values read from it.
+    const uint32_t ring0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_ring)) + (warp * kAhead * kWarp + lane) * kSlot;
 #pragma unroll
     for (int j = 0; j < kAhead; ++j) {
-        qmask[j] = false;
-        q[j][0] = q[j][1] = q[j][2] = q[j][3] = T(0);
         const int lr = group + j * groups;
-        if (lr < nrows) {
-            load4(xcol + static_cast<size_t>(src_row(r0 + lr)) * f.ldx, q[j][0], q[j][1], q[j][2], q[j][3]);
-            if (any_mask) qmask[j] = f.row_mask[r0 + lr] != 0;
-        }
+        if (lr < nrows) ring_fetch(ring0 + j * (kWarp * kSlot), xcol + static_cast<size_t>(src_row(r0 + lr)) * f.ldx);
+        cp_async_commit();  // one group per row, empty or not, so the wait below counts rows
     }
+    uint32_t slot = ring0;
+    const uint32_t ring_end = ring0 + kAhead * (kWarp * kSlot);
 #pragma unroll 1
     for (int lr = group; lr < nrows; lr += groups) {
         const long long row = r0 + lr;
-        const T a0 = q[0][0], a1 = q[0][1], a2 = q[0][2], a3 = q[0][3];
-        const bool masked = qmask[0];
-#pragma unroll
-        for (int j = 0; j + 1 < kAhead; ++j) {
-            q[j][0] = q[j + 1][0], q[j][1] = q[j + 1][1], q[j][2] = q[j + 1][2], q[j][3] = q[j + 1][3];
-            qmask[j] = qmask[j + 1];
-        }
-        if (lr + kAhead * groups < nrows) {
-            load4(xcol + static_cast<size_t>(src_row(row + kAhead * groups)) * f.ldx, q[kAhead - 1][0], q[kAhead - 1][1], q[kAhead - 1][2], q[kAhead - 1][3]);
-            if (any_mask) qmask[kAhead - 1] = f.row_mask[row + kAhead * groups] != 0;
-        }
+        T a0, a1, a2, a3;
+        cp_async_wait<kAhead - 1>();
+        ring_read(slot, a0, a1, a2, a3);
+        const bool masked = any_mask && s_mask[lr] != 0;
         epilogue_store<T, true, FAM>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
+        const int nxt = lr + kAhead * groups;
+        if (nxt < nrows) ring_fetch(slot, xcol + static_cast<size_t>(src_row(r0 + nxt)) * f.ldx);
+        cp_async_commit();
+        slot += kWarp * kSlot;
+        if (slot == ring_end) slot = ring0;
     }
 }
 
@@ -1165,9 +1197,9 @@ static int launch_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void
     f.ldx = static_cast<size_t>(ldx);
     f.ldy = static_cast<size_t>(ldy);
     f.n_rows = n_rows;
-    f.rows_per_cta = 32;
+    f.rows_per_cta = kPwCtaRows;
     f.n_tiles = epi->n_tiles;
-    const int64_t gx = (n_rows + f.rows_per_cta - 1) / f.rows_per_cta;
+    const int64_t gx = (n_rows + kPwCtaRows - 1) / kPwCtaRows;
     if (gx >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_pointwise: too many rows");
     dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((epi->n_tiles + kWarps - 1) / kWarps));
     if ((epi->kinds_mask & ~FAM_BASIC) == 0)
