@@ -24,6 +24,7 @@
 //     __fmul_rn / __fadd_rn (never contracted to FMA);
 //   - Y is write-once: streaming stores (st.global.cs).
 #include <algorithm>
+#include <type_traits>
 #include <cmath>
 #include <mutex>
 #include <vector>
@@ -426,31 +427,70 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
 
     const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
     if (group >= nrows) return;
-    // Transcendental kinds: one copy of the epilogue code behind a ring of kAhead rows in flight.
-    // Slot k of a lane is refilled only after the epilogue has consumed the values read from it.
+    // Transcendental kinds: a ring of kAhead rows in flight behind the epilogue.  The kind is
+    // dispatched once per warp, outside the row loop, so each loop is compiled for its kind (no
+    // switch per row, row-invariant range tests hoisted) and every kind's code still exists once.
+    // Addresses advance by additions; slot k of a lane is refilled only after the epilogue has
+    // consumed the values read from it.
     const uint32_t ring0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_ring)) + (warp * kAhead * kWarp + lane) * kSlot;
-#pragma unroll
-    for (int j = 0; j < kAhead; ++j) {
-        const int lr = group + j * groups;
-        if (lr < nrows) ring_fetch(ring0 + j * (kWarp * kSlot), xcol + static_cast<size_t>(src_row(r0 + lr)) * f.ldx);
-        cp_async_commit();  // one group per row, empty or not, so the wait below counts rows
-    }
-    uint32_t slot = ring0;
     const uint32_t ring_end = ring0 + kAhead * (kWarp * kSlot);
+    const uint32_t smask0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_mask)) + group;
+    auto rows = [&](auto kind_c) {
+        EpiTile tk = tile;
+        tk.kind = decltype(kind_c)::value;
+#pragma unroll
+        for (int j = 0; j < kAhead; ++j) {
+            const int lr = group + j * groups;
+            if (lr < nrows) ring_fetch(ring0 + j * (kWarp * kSlot), xcol + static_cast<size_t>(src_row(r0 + lr)) * f.ldx);
+            cp_async_commit();  // one group per row, empty or not, so the wait below counts rows
+        }
+        uint32_t slot = ring0, smask = smask0;
+        const size_t xstep = static_cast<size_t>(groups) * f.ldx, ystep = static_cast<size_t>(groups) * f.ldy;
+        const T* xnext = xcol + static_cast<size_t>(r0 + group + kAhead * groups) * f.ldx;  // the row the ring asks for next (no gather)
+        T* yrow = f.Y + static_cast<size_t>(r0 + group) * f.ldy;
 #pragma unroll 1
-    for (int lr = group; lr < nrows; lr += groups) {
-        const long long row = r0 + lr;
-        T a0, a1, a2, a3;
-        cp_async_wait<kAhead - 1>();
-        ring_read(slot, a0, a1, a2, a3);
-        const bool masked = any_mask && s_mask[lr] != 0;
-        epilogue_store<T, true, FAM>(tile, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, f.Y + static_cast<size_t>(row) * f.ldy, &clip);
-        const int nxt = lr + kAhead * groups;
-        if (nxt < nrows) ring_fetch(slot, xcol + static_cast<size_t>(src_row(r0 + nxt)) * f.ldx);
-        cp_async_commit();
-        slot += kWarp * kSlot;
-        if (slot == ring_end) slot = ring0;
+        for (int lr = group; lr < nrows; lr += groups) {
+            T a0, a1, a2, a3;
+            cp_async_wait<kAhead - 1>();
+            ring_read(slot, a0, a1, a2, a3);
+            bool masked = false;
+            if (any_mask) {
+                uint32_t m;
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(smask));
+                masked = m != 0;
+            }
+            epilogue_store<T, true, FAM>(tk, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, yrow, &clip);
+            const int nxt = lr + kAhead * groups;
+            if (nxt < nrows) ring_fetch(slot, rix != nullptr ? xcol + static_cast<size_t>(__ldg(rix + r0 + nxt)) * f.ldx : xnext);
+            cp_async_commit();
+            xnext += xstep, yrow += ystep, smask += groups;
+            slot += kWarp * kSlot;
+            if (slot == ring_end) slot = ring0;
+        }
+    };
+#define AT_PW_KIND(K)                                                          \
+    case K:                                                                    \
+        if constexpr ((FAM & kind_bit(K)) != 0) rows(std::integral_constant<int, K>{}); \
+        break;
+    switch (tile.kind) {
+        AT_PW_KIND(AT_EPI_UV2DDFF)
+        AT_PW_KIND(AT_EPI_DDFF2UV)
+        AT_PW_KIND(AT_EPI_QT2R)
+        AT_PW_KIND(AT_EPI_QT2QTR)
+        AT_PW_KIND(AT_EPI_RT2Q)
+        AT_PW_KIND(AT_EPI_RT2RTQ)
+        AT_PW_KIND(AT_EPI_EXP)
+        AT_PW_KIND(AT_EPI_LOG)
+        AT_PW_KIND(AT_EPI_COSSIN)
+        AT_PW_KIND(AT_EPI_ATAN2)
+        AT_PW_KIND(AT_EPI_RT2D)
+        AT_PW_KIND(AT_EPI_RT2RTD)
+        AT_PW_KIND(AT_EPI_DT2R)
+        AT_PW_KIND(AT_EPI_DT2DTR)
+        default:
+            break;
     }
+#undef AT_PW_KIND
 }
 
 // ---- generic dtypes (float64 matrix and / or float64 fields): scalar columns ----------

@@ -3,11 +3,15 @@
 ms, algorithmic GB/s and the fraction of the measured HBM peak.  CUDA events, warm, best of 5.
 
     python benchmarks/epi_kinds.py [--json out.json]
+    AT_UNDER_NCU=1 ncu --set full -k regex:pointwise_kernel … python benchmarks/epi_kinds.py
+        one launch per (kind, flags), in the order of the table — numbers printed under ncu
+        are not bench values
 """
 
 from __future__ import annotations
 
 import json
+import os
 import sys
 from pathlib import Path
 
@@ -59,6 +63,11 @@ def main():
         for fl_name, fl in (("noflags", 0), ("clip+mask", CL | CH | MK)):
             epi = Epilogue([(kind, 0, F, 0, 1.0, 0.0)], [(-1e30, 1e30, 85000.0, fl)] * nout)
             Y = torch.empty((n, (nout + 3) // 4 * 4), device="cuda")
+            if os.environ.get("AT_UNDER_NCU"):
+                epi.apply(x, out=Y, row_mask=mask)
+                torch.cuda.synchronize()
+                print(f"launched {name} {fl_name}", flush=True)
+                continue
             ms = dev_ms(lambda: epi.apply(x, out=Y, row_mask=mask))
             gbs = 4 * n * (F + nout) / ms / 1e6
             rows.append({"kind": name, "flags": fl_name, "ms": ms, "algorithmic_GBps": gbs, "frac_of_measured_peak": gbs / peak})
