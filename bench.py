@@ -16,6 +16,9 @@ One JSON line on stdout (rank 0):
                   create_filter_by_name("regrid", matrix=…).forward(FieldList of ordinary numpy
                   fields) + to_numpy() of every output — host staging, H2D, kernels and D2H all
                   inside the timed region
+    e2e_pinned_fields  the same plugin call on fields whose numpy arrays live in page-locked memory
+                  (device.pinned_empty — what a decoder that feeds these filters allocates): no
+                  staging copy
     e2e_cabi      the same bytes through the bare C-ABI pipeline (at_pipeline_regrid) with
                   caller-pinned buffers: the PCIe floor the plugin path is measured against
     pipeline_e2e  config 4 as a FieldList pipeline (regrid | uv_to_ddff | q_to_r | clip |
@@ -266,18 +269,27 @@ def make_fieldlist(values, lat, lon, specs=None):
     return ekd.from_source("list-of-dicts", [dict(values=v, latitudes=lat, longitudes=lon, **s) for v, s in zip(values, specs)])
 
 
-def plugin_e2e(w, matrix_path, n_local: int, steps: int, rank: int, barrier, max_over_ranks) -> dict:
+def plugin_e2e(w, matrix_path, n_local: int, steps: int, rank: int, barrier, max_over_ranks, page_locked: bool = False) -> dict | None:
     """FieldList of ordinary (pageable) numpy fields → RegridFilter.forward → to_numpy() of
-    every output.  Each field is its own numpy array, as a decoder would deliver them."""
+    every output.  Each field is its own numpy array, as a decoder would deliver them.
+    `page_locked`: the same call on fields whose arrays a decoder allocated with
+    `device.pinned_empty` (numpy arrays in page-locked memory): no staging copy, H2D in place."""
     from anemoi_transform_b200 import synthetic as syn
-    from anemoi_transform_b200.device import HostIO
+    from anemoi_transform_b200.device import HostIO, pinned_fields
     from anemoi_transform_b200.filters import create_filter_by_name
 
     n_tgt, n_src = w["shape"]
     s_lat, s_lon = syn.regular_latlon(0.25)
     rng = np.random.default_rng(99 + rank)
     base = rng.standard_normal((min(64, n_local), n_src), dtype=np.float32)
-    values = [np.array(base[k % base.shape[0]]) for k in range(n_local)]
+    if page_locked:
+        values, _ = pinned_fields(n_local, n_src, np.float32)
+        if values is None:
+            return None
+        for k, v in enumerate(values):
+            v[:] = base[k % base.shape[0]]
+    else:
+        values = [np.array(base[k % base.shape[0]]) for k in range(n_local)]
     fl = make_fieldlist(values, s_lat, s_lon)
     regrid = create_filter_by_name("regrid", matrix=matrix_path)
 
@@ -304,7 +316,10 @@ def plugin_e2e(w, matrix_path, n_local: int, steps: int, rank: int, barrier, max
         "seconds": seconds,
         "parity_spot_check": parity,
         "staging_threads": io.n_threads,
-        "path": "create_filter_by_name('regrid', matrix=...).forward(FieldList of pageable numpy fields) + to_numpy() of every output: "
+        "path": "create_filter_by_name('regrid', matrix=...).forward(FieldList of numpy fields in page-locked memory (device.pinned_empty)) + to_numpy() of every output: "
+        "H2D straight from the caller's arrays -> pack -> SpMM -> unpack -> D2H straight into the page-locked arrays the caller receives"
+        if page_locked
+        else "create_filter_by_name('regrid', matrix=...).forward(FieldList of pageable numpy fields) + to_numpy() of every output: "
         "worker threads stage the fields into pinned slots -> H2D -> pack -> SpMM -> unpack -> D2H straight into the page-locked arrays the caller receives",
     }
 
@@ -734,7 +749,30 @@ def run_gpu(args):
     }
     import gc
 
+    from anemoi_transform_b200.device import pinned_pool_trim
+
     gc.collect()
+    e2e_pinned = None
+    try:  # an extra leg: it must not take the headline line down with it
+        plug_pl = plugin_e2e(w, matrix_path, n_local, max(1, min(2, e2e_steps)), rank, barrier, max_over_ranks, page_locked=True)
+        if plug_pl is not None:
+            e2e_pinned = {
+                "value": N_FIELDS / plug_pl["seconds"],
+                "unit": "fields/s",
+                "ms_per_step": plug_pl["seconds"] * 1e3,
+                "h2d_bytes_per_step": 4 * N_FIELDS * n_src,
+                "d2h_bytes_per_step": 4 * N_FIELDS * n_tgt,
+                "path": plug_pl["path"],
+                "parity_spot_check": plug_pl["parity_spot_check"],
+            }
+        del plug_pl
+    except Exception as e:  # noqa: BLE001
+        if world > 1:
+            raise  # the other ranks are inside its barriers
+        log("e2e_pinned_fields leg failed:", repr(e))
+        e2e_pinned = {"error": repr(e)}
+    gc.collect()
+    pinned_pool_trim()
     cabi = cabi_e2e(csr, w, n_local, max(1, min(2, e2e_steps)), args.chunk, rank, world, barrier, max_over_ranks)
     e2e_cabi = {
         "value": N_FIELDS / cabi["seconds"],
@@ -783,6 +821,7 @@ def run_gpu(args):
             "spmm_variant": args.variant,
             "clocks": clocks,
             "e2e": e2e,
+            "e2e_pinned_fields": e2e_pinned,
             "e2e_cabi": e2e_cabi,
             "pipeline_e2e": pipe4,
             "e2e_grib": grib_leg,
