@@ -284,7 +284,7 @@ def plugin_e2e(w, matrix_path, n_local: int, steps: int, rank: int, barrier, max
     base = rng.standard_normal((min(64, n_local), n_src), dtype=np.float32)
     if page_locked:
         values, _ = pinned_fields(n_local, n_src, np.float32)
-        if values is None:
+        if max_over_ranks(1.0 if values is None else 0.0) > 0.0:  # every rank or none: barriers follow
             return None
         for k, v in enumerate(values):
             v[:] = base[k % base.shape[0]]
