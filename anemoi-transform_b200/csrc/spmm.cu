@@ -435,10 +435,17 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     const int groups = kWarps / t_here, group = warp / t_here;
     if (group >= groups) return;
     const EpiTile tile = f.tiles[blockIdx.y * kWarps + warp % t_here];
-    if (lane >= tile.n_vec) return;
+    // A tile narrower than half a warp (the ragged end of a segment: 520 columns are four full
+    // tiles and one of 2 lanes) packs several rows into the warp instead of idling its lanes:
+    // lane -> (column group v, row sub) with `rpw` rows per warp step.
+    int vbits = 5;
+    while (vbits > 0 && (1 << (vbits - 1)) >= tile.n_vec) --vbits;
+    const int v = lane & ((1 << vbits) - 1), sub = lane >> vbits, rpw = kWarp >> vbits;
+    if (v >= tile.n_vec) return;
+    const int rfirst = group * rpw + sub, rstep = groups * rpw;  // this lane's rows: rfirst, rfirst + rstep, ...
     const bool any_mask = f.row_mask != nullptr && (tile.flags_any & AT_COL_MASK) != 0;
-    const T* xcol = f.X + 4 * static_cast<size_t>(tile.in_vec0 + lane);
-    const EpiClip<T> clip = epilogue_prepare_clip<T>(tile, lane, f.cols);
+    const T* xcol = f.X + 4 * static_cast<size_t>(tile.in_vec0 + v);
+    const EpiClip<T> clip = epilogue_prepare_clip<T>(tile, v, f.cols);
     // nearest-neighbour / masked regrid fused with the pointwise program: a row gather on the way in
     const long long* __restrict__ rix = f.row_index;
     auto src_row = [rix](long long r) { return rix != nullptr ? __ldg(rix + r) : r; };
@@ -448,28 +455,28 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     constexpr uint32_t kCopyLike = kind_bit(AT_EPI_PLAIN) | kind_bit(AT_EPI_AFFINE) | kind_bit(AT_EPI_AFFINE_INV) | kind_bit(AT_EPI_IMPUTE_NAN);
     if ((kind_bit(tile.kind) & kCopyLike) != 0) {
         const EpiLane<T> none = {T(0), T(0)};
-        for (int lr = group * kPwRows; lr < nrows; lr += groups * kPwRows) {
+        for (int lr = rfirst; lr < nrows; lr += rstep * kPwRows) {
             T a[kPwRows][4];
             bool masked[kPwRows];
 #pragma unroll
             for (int j = 0; j < kPwRows; ++j) {
                 masked[j] = false;
-                if (lr + j < nrows) {
-                    load4(xcol + static_cast<size_t>(src_row(r0 + lr + j)) * f.ldx, a[j][0], a[j][1], a[j][2], a[j][3]);
-                    if (any_mask) masked[j] = s_mask[lr + j] != 0;
+                if (lr + j * rstep < nrows) {
+                    load4(xcol + static_cast<size_t>(src_row(r0 + lr + j * rstep)) * f.ldx, a[j][0], a[j][1], a[j][2], a[j][3]);
+                    if (any_mask) masked[j] = s_mask[lr + j * rstep] != 0;
                 }
             }
 #pragma unroll
             for (int j = 0; j < kPwRows; ++j)
-                if (lr + j < nrows)
-                    epilogue_store<T, true, FAM & kCopyLike>(tile, lane, a[j][0], a[j][1], a[j][2], a[j][3], none, f.cols, masked[j],
-                                                            f.Y + static_cast<size_t>(r0 + lr + j) * f.ldy, &clip);
+                if (lr + j * rstep < nrows)
+                    epilogue_store<T, true, FAM & kCopyLike>(tile, v, a[j][0], a[j][1], a[j][2], a[j][3], none, f.cols, masked[j],
+                                                            f.Y + static_cast<size_t>(r0 + lr + j * rstep) * f.ldy, &clip);
         }
         return;
     }
 
-    const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, lane, f.cols);
-    if (group >= nrows) return;
+    const EpiLane<T> lane_prm = epilogue_prepare<T>(tile, v, f.cols);
+    if (rfirst >= nrows) return;
     // Transcendental kinds: a ring of kAhead rows in flight behind the epilogue.  The kind is
     // dispatched once per warp, outside the row loop, so each loop is compiled for its kind (no
     // switch per row, row-invariant range tests hoisted) and every kind's code still exists once.
@@ -477,22 +484,22 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     // consumed the values read from it.
     const uint32_t ring0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_ring)) + (warp * kAhead * kWarp + lane) * kSlot;
     const uint32_t ring_end = ring0 + kAhead * (kWarp * kSlot);
-    const uint32_t smask0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_mask)) + group;
+    const uint32_t smask0 = static_cast<uint32_t>(__cvta_generic_to_shared(s_mask)) + rfirst;
     auto rows = [&](auto kind_c) {
         EpiTile tk = tile;
         tk.kind = decltype(kind_c)::value;
 #pragma unroll
         for (int j = 0; j < kAhead; ++j) {
-            const int lr = group + j * groups;
+            const int lr = rfirst + j * rstep;
             if (lr < nrows) ring_fetch(ring0 + j * (kWarp * kSlot), xcol + static_cast<size_t>(src_row(r0 + lr)) * f.ldx);
             cp_async_commit();  // one group per row, empty or not, so the wait below counts rows
         }
         uint32_t slot = ring0, smask = smask0;
-        const size_t xstep = static_cast<size_t>(groups) * f.ldx, ystep = static_cast<size_t>(groups) * f.ldy;
-        const T* xnext = xcol + static_cast<size_t>(r0 + group + kAhead * groups) * f.ldx;  // the row the ring asks for next (no gather)
-        T* yrow = f.Y + static_cast<size_t>(r0 + group) * f.ldy;
+        const size_t xstep = static_cast<size_t>(rstep) * f.ldx, ystep = static_cast<size_t>(rstep) * f.ldy;
+        const T* xnext = xcol + static_cast<size_t>(r0 + rfirst + kAhead * rstep) * f.ldx;  // the row the ring asks for next (no gather)
+        T* yrow = f.Y + static_cast<size_t>(r0 + rfirst) * f.ldy;
 #pragma unroll 1
-        for (int lr = group; lr < nrows; lr += groups) {
+        for (int lr = rfirst; lr < nrows; lr += rstep) {
             T a0, a1, a2, a3;
             cp_async_wait<kAhead - 1>();
             ring_read(slot, a0, a1, a2, a3);
@@ -502,11 +509,11 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(smask));
                 masked = m != 0;
             }
-            epilogue_store<T, true, FAM>(tk, lane, a0, a1, a2, a3, lane_prm, f.cols, masked, yrow, &clip);
-            const int nxt = lr + kAhead * groups;
+            epilogue_store<T, true, FAM>(tk, v, a0, a1, a2, a3, lane_prm, f.cols, masked, yrow, &clip);
+            const int nxt = lr + kAhead * rstep;
             if (nxt < nrows) ring_fetch(slot, rix != nullptr ? xcol + static_cast<size_t>(__ldg(rix + r0 + nxt)) * f.ldx : xnext);
             cp_async_commit();
-            xnext += xstep, yrow += ystep, smask += groups;
+            xnext += xstep, yrow += ystep, smask += rstep;
             slot += kWarp * kSlot;
             if (slot == ring_end) slot = ring0;
         }

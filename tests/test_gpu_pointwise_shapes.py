@@ -76,7 +76,7 @@ KINDS = {
 
 @pytest.mark.parametrize("kind_name", sorted(KINDS))
 @pytest.mark.parametrize("n_rows", [1, 2, 3, 5, 31, 32, 33, 97])
-@pytest.mark.parametrize("n_cols", [8, 136, 1032])
+@pytest.mark.parametrize("n_cols", [8, 40, 136, 1032])
 def test_rows_do_not_depend_on_the_launch_shape(cuda, kind_name, n_rows, n_cols):
     import torch
 
@@ -141,3 +141,28 @@ def test_ring_with_row_gather_mask_and_clip(cuda, dtype):
     assert np.abs(got[:, 0::2][ok] - ws[ok]).max() <= tol * 8.0
     d = np.abs(got[:, 1::2].astype(np.float64) - wd)
     assert np.minimum(d, 360.0 - d).max() <= 360 * tol
+
+
+@pytest.mark.parametrize("n_cols", [4, 8, 40, 68, 136])
+@pytest.mark.parametrize("n_rows", [1, 7, 32, 33, 200])
+def test_copy_like_tiles_pack_rows_into_narrow_warps(cuda, n_rows, n_cols):
+    """clip + mask (np.clip, values[mask] = nan — clipper.py:69, apply_mask.py:185) on column
+    counts whose last tile is narrower than half a warp: exact."""
+    import torch
+
+    from anemoi_transform_b200 import _cabi
+    from anemoi_transform_b200.device import Epilogue
+
+    rng = np.random.default_rng(n_rows * 100 + n_cols)
+    x = rng.standard_normal((n_rows, n_cols)).astype(np.float32)
+    x[rng.random(x.shape) < 0.01] = np.nan
+    mask = (rng.random(n_rows) < 0.3).astype(np.uint8)
+    CL, CH, MK = _cabi.COL_CLIP_LO, _cabi.COL_CLIP_HI, _cabi.COL_MASK
+    cols = [(-0.5, 0.75, 0.0, CL | CH | (MK if c % 3 == 0 else 0)) for c in range(n_cols)]
+    epi = Epilogue([(_cabi.EPI_PLAIN, 0, n_cols, 0, 1.0, 0.0)], cols)
+    got = epi.apply(torch.from_numpy(x).cuda(), row_mask=torch.from_numpy(mask).cuda()).cpu().numpy()[:, :n_cols]
+    want = np.clip(x, np.float32(-0.5), np.float32(0.75))
+    want[np.ix_(mask != 0, np.arange(n_cols) % 3 == 0)] = np.nan
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32))
