@@ -284,14 +284,21 @@ __global__ void __launch_bounds__(kThreads, 4) spmm_fused_kernel(const FusedArgs
     if (t_index >= a.n_vec) return;  // n_vec = number of tile-table entries here
 
     const EpiTile tile = f.tiles[t_index];
-    int vcol[1] = {tile.in_vec0 + lane};
-    bool vok[1] = {lane < tile.n_vec};
+    // A tile narrower than half a warp (the ragged end of a segment) packs several target rows
+    // into the warp, lane -> (column group v, row sub), instead of idling its lanes; every lane
+    // then walks the CSR entries of its own row.
+    int vbits = 5;
+    while (vbits > 0 && (1 << (vbits - 1)) >= tile.n_vec) --vbits;
+    const int v = lane & ((1 << vbits) - 1), rpw = kWarp >> vbits;
+    const int rfirst = warp * rpw + (lane >> vbits), rstep = kWarps * rpw;  // this lane's rows
+    int vcol[1] = {tile.in_vec0 + v};
+    bool vok[1] = {v < tile.n_vec};
 
     int seg_base;
     bool in_smem;
     stage_segment<UNNZ, UNNZ != 0, FALLBACK>(a, r0, nrows, s_ptr, s_idx, s_w, &s_bar, seg_base, in_smem);
 
-    const EpiLane<float> lane_prm = epilogue_prepare<float>(tile, lane, f.cols);
+    const EpiLane<float> lane_prm = epilogue_prepare<float>(tile, v, f.cols);
     const bool any_mask = (tile.flags_any & AT_COL_MASK) != 0 && f.row_mask != nullptr;
 
     // The kind is CTA-uniform: dispatch it once, outside the row loop, so each loop is compiled for
@@ -299,9 +306,9 @@ __global__ void __launch_bounds__(kThreads, 4) spmm_fused_kernel(const FusedArgs
     auto rows = [&](auto kind_c) {
         EpiTile tk = tile;
         if constexpr (decltype(kind_c)::value >= 0) tk.kind = decltype(kind_c)::value;
-        float* yrow = f.Yf + static_cast<size_t>(r0 + warp) * f.ldy;
-        const size_t ystep = static_cast<size_t>(kWarps) * f.ldy;
-        for (int lr = warp; lr < nrows; lr += kWarps, yrow += ystep) {
+        float* yrow = f.Yf + static_cast<size_t>(r0 + rfirst) * f.ldy;
+        const size_t ystep = static_cast<size_t>(rstep) * f.ldy;
+        for (int lr = rfirst; lr < nrows; lr += rstep, yrow += ystep) {
             float4 acc[1] = {make_float4(0.f, 0.f, 0.f, 0.f)};
             if constexpr (UNNZ > 0) {
                 accumulate_row<1, 4, true>(a, lr * UNNZ, (lr + 1) * UNNZ, s_idx, s_w, vcol, vok, acc);
@@ -319,12 +326,12 @@ __global__ void __launch_bounds__(kThreads, 4) spmm_fused_kernel(const FusedArgs
             // whose re-referenced source rows already sit in L2, the extra instructions cost
             // 5 % (3.19 -> 3.34 ms on a 2/3-transcendental program), so those do not prefetch.
             if constexpr (UNNZ >= 8) {
-                if (lr + kWarps < nrows && vok[0]) {
+                if (lr + rstep < nrows && vok[0]) {
 #pragma unroll
-                    for (int j = 0; j < UNNZ; ++j) prefetch_l2(a.X + static_cast<size_t>(s_idx[(lr + kWarps) * UNNZ + j]) * a.ldx4 + vcol[0]);
+                    for (int j = 0; j < UNNZ; ++j) prefetch_l2(a.X + static_cast<size_t>(s_idx[(lr + rstep) * UNNZ + j]) * a.ldx4 + vcol[0]);
                 }
             }
-            if (vok[0]) epilogue_store<float, false, FAM>(tk, lane, acc[0].x, acc[0].y, acc[0].z, acc[0].w, lane_prm, f.cols, masked, yrow);
+            if (vok[0]) epilogue_store<float, false, FAM>(tk, v, acc[0].x, acc[0].y, acc[0].z, acc[0].w, lane_prm, f.cols, masked, yrow);
         }
     };
 #define AT_FUSED_KIND(K)                                                       \

@@ -166,3 +166,44 @@ def test_copy_like_tiles_pack_rows_into_narrow_warps(cuda, n_rows, n_cols):
     assert np.array_equal(np.isnan(got), np.isnan(want))
     ok = ~np.isnan(want)
     assert np.array_equal(got[ok].view(np.uint32), want[ok].view(np.uint32))
+
+
+@pytest.mark.parametrize("nnz_per_row", [4, 12, 0])
+@pytest.mark.parametrize("n_cols", [8, 40, 136, 264])
+def test_fused_narrow_tiles_equal_the_unfused_chain(cuda, nnz_per_row, n_cols):
+    """spmm_fused_kernel packs several target rows into a warp when a tile is narrower than half
+    a warp (every lane walks its own row's CSR entries): bitwise the SpMM followed by the
+    standalone epilogue, on uniform 4- and 12-nonzero rows and on ragged rows (0 = rows of 0..9
+    entries, empty rows included)."""
+    import torch
+    from scipy.sparse import csr_array
+
+    from anemoi_transform_b200 import _cabi
+    from anemoi_transform_b200.device import CsrMatrix, Epilogue
+
+    rng = np.random.default_rng(nnz_per_row * 1000 + n_cols)
+    n_tgt, n_src = 333, 517
+    lengths = np.full(n_tgt, nnz_per_row) if nnz_per_row else rng.integers(0, 10, n_tgt)
+    indptr = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    indices = np.concatenate([np.sort(rng.choice(n_src, k, replace=False)) for k in lengths] + [np.empty(0, np.int64)]).astype(np.int32)
+    data = rng.random(indices.size).astype(np.float32)
+    x = (rng.standard_normal((n_src, n_cols)) * 8.0).astype(np.float32)
+    mask = (rng.random(n_tgt) < 0.3).astype(np.uint8)
+    CL, CH, MK = _cabi.COL_CLIP_LO, _cabi.COL_CLIP_HI, _cabi.COL_MASK
+    half = n_cols // 8 * 4  # first half (u, v) -> (ws, wdir), second half clip + mask only
+    segs = [(_cabi.EPI_UV2DDFF, 0, half, 0), (_cabi.EPI_PLAIN, half, n_cols - half, half)]
+    cols = [(0.5, 30.0, 0.0, CL | CH | MK), (0.0, 0.0, 0.0, 0)] * (half // 2) + [(-4.0, 4.0, 0.0, CL | CH | MK)] * (n_cols - half)
+    epi = Epilogue(segs, cols)
+    csr = CsrMatrix(data, indices, indptr, (n_tgt, n_src))
+    X = torch.from_numpy(x).cuda()
+    M = torch.from_numpy(mask).cuda()
+    fused = epi.apply_fused(csr, X, row_mask=M).cpu().numpy()[:, :n_cols]
+    y = csr.apply(X, n_fields=n_cols)
+    unfused = epi.apply(y, row_mask=M).cpu().numpy()[:, :n_cols]
+    assert np.array_equal(np.isnan(fused), np.isnan(unfused))
+    ok = ~np.isnan(fused)
+    assert np.array_equal(fused[ok].view(np.uint32), unfused[ok].view(np.uint32))
+    # and the SpMM half against scipy, bit for bit
+    want = np.stack([csr_array((data, indices, indptr), shape=(n_tgt, n_src)) @ x[:, c] for c in (0, n_cols - 1)], axis=1)
+    got = y.cpu().numpy()[:, [0, n_cols - 1]]
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
