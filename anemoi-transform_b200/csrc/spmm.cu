@@ -306,6 +306,13 @@ __global__ void __launch_bounds__(kThreads, 4) spmm_fused_kernel(const FusedArgs
     auto rows = [&](auto kind_c) {
         EpiTile tk = tile;
         if constexpr (decltype(kind_c)::value >= 0) tk.kind = decltype(kind_c)::value;
+        // Clip bounds and mask bits of the lane's outputs in registers (the kind is known here, so
+        // only its outputs' bounds stay live) instead of a read of the per-column table per row and
+        // output: 2.91 -> 2.44 ms on a program with flags on every column.  The 12-nonzero
+        // instantiation has no registers to spare (it spills more and loses 1 %): it keeps the reads.
+        constexpr bool kHoist = UNNZ < 8;
+        EpiClip<float> clip;
+        if constexpr (kHoist) clip = epilogue_prepare_clip<float>(tk, v, f.cols);
         float* yrow = f.Yf + static_cast<size_t>(r0 + rfirst) * f.ldy;
         const size_t ystep = static_cast<size_t>(rstep) * f.ldy;
         for (int lr = rfirst; lr < nrows; lr += rstep, yrow += ystep) {
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 4) spmm_fused_kernel(const FusedArgs
                     for (int j = 0; j < UNNZ; ++j) prefetch_l2(a.X + static_cast<size_t>(s_idx[(lr + rstep) * UNNZ + j]) * a.ldx4 + vcol[0]);
                 }
             }
-            if (vok[0]) epilogue_store<float, false, FAM>(tk, v, acc[0].x, acc[0].y, acc[0].z, acc[0].w, lane_prm, f.cols, masked, yrow);
+            if (vok[0]) epilogue_store<float, kHoist, FAM>(tk, v, acc[0].x, acc[0].y, acc[0].z, acc[0].w, lane_prm, f.cols, masked, yrow, &clip);
         }
     };
 #define AT_FUSED_KIND(K)                                                       \
