@@ -427,7 +427,9 @@ __device__ __forceinline__ void load4(const double* p, double& a, double& b, dou
 // of loads in flight in registers; transcendental tiles, which have no registers to spare at the
 // 64-register cap (4 CTAs per SM), keep kPwAhead rows in flight in shared memory instead —
 // cp.async (LDGSTS) into a per-lane ring, 16 bytes per lane and row, read back by the lane that
-// copied them (no barrier, no bank conflict) — behind one copy of the epilogue code.
+// copied them (no barrier, no bank conflict) — behind a row loop compiled once per kind.
+// (Measured, profiles/r02_pw_ring_depth_sweep.log: 1 / 2 / 4 rows in flight -> uv_to_ddff 0.60 /
+// 0.81 / 0.87 of the HBM peak, 6 and 8 add nothing; the per-kind loops then reach 1.00.)
 constexpr int kPwRows = 4;
 constexpr int kPwCtaRows = 32;  // rows per CTA (launch_pointwise)
 #ifndef AT_PW_AHEAD
