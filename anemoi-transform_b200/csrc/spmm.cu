@@ -407,6 +407,7 @@ struct PointwiseArgs {
     long long n_rows;
     int rows_per_cta;
     int n_tiles;
+    int uses_es;  // the program has a (q, t) <-> r kind: stage the es(T) table in shared memory
 };
 
 __device__ __forceinline__ void load4(const float* p, float& a, float& b, float& c, float& d) {
@@ -465,11 +466,17 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     constexpr int kAhead = sizeof(T) == 4 ? kPwAhead : (kPwAhead < 4 ? kPwAhead : 4);  // float64: 2 CTAs per SM of twice the bytes
     __shared__ __align__(16) unsigned char s_ring[kWarps * kAhead * kWarp * kSlot];
     __shared__ uint8_t s_mask[kPwCtaRows];
+    // es(T) cubics of the float32 humidity fast paths (epilogue.cuh): 32 lanes look up 32 different
+    // entries, which costs the L1 up to 32 sectors per warp load and shared memory a few wavefronts
+    __shared__ __align__(16) float4 s_es[sizeof(T) == 4 ? kEsTableN : 1];
     const long long r0 = static_cast<long long>(blockIdx.x) * kPwCtaRows;
     const int nrows = static_cast<int>(min(static_cast<long long>(kPwCtaRows), f.n_rows - r0));
-    // the CTA's slice of the row mask, once (before any warp leaves: every thread reaches the barrier)
-    if (f.row_mask != nullptr) {
-        if (threadIdx.x < nrows) s_mask[threadIdx.x] = f.row_mask[r0 + threadIdx.x];
+    // the CTA's slice of the row mask and the table, once (before any warp leaves: every thread reaches the barrier)
+    const bool stage_es = sizeof(T) == 4 && f.uses_es != 0;
+    if (f.row_mask != nullptr || stage_es) {
+        if (f.row_mask != nullptr && threadIdx.x < nrows) s_mask[threadIdx.x] = f.row_mask[r0 + threadIdx.x];
+        if (stage_es)
+            for (int i = threadIdx.x; i < kEsTableN; i += kThreads) s_es[i] = g_es_mixed_table[i];
         __syncthreads();
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -532,6 +539,9 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
     auto rows = [&](auto kind_c) {
         EpiTile tk = tile;
         tk.kind = decltype(kind_c)::value;
+        EpiLane<T> lp = lane_prm;
+        constexpr int K = decltype(kind_c)::value;
+        if constexpr (sizeof(T) == 4 && (K == AT_EPI_QT2R || K == AT_EPI_QT2QTR || K == AT_EPI_RT2Q || K == AT_EPI_RT2RTQ)) lp.es_table = s_es;
 #pragma unroll
         for (int j = 0; j < kAhead; ++j) {
             const int lr = rfirst + j * rstep;
@@ -553,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2) pointwise_ke
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(m) : "r"(smask));
                 masked = m != 0;
             }
-            epilogue_store<T, true, FAM>(tk, v, a0, a1, a2, a3, lane_prm, f.cols, masked, yrow, &clip);
+            epilogue_store<T, true, FAM>(tk, v, a0, a1, a2, a3, lp, f.cols, masked, yrow, &clip);
             const int nxt = lr + kAhead * rstep;
             if (nxt < nrows) ring_fetch(slot, rix != nullptr ? xcol + static_cast<size_t>(__ldg(rix + r0 + nxt)) * f.ldx : xnext);
             cp_async_commit();
@@ -1333,6 +1343,7 @@ static int launch_pointwise(const at_epilogue_t* epi, int64_t n_rows, const void
     f.n_rows = n_rows;
     f.rows_per_cta = kPwCtaRows;
     f.n_tiles = epi->n_tiles;
+    f.uses_es = (epi->kinds_mask & (kind_bit(AT_EPI_QT2R) | kind_bit(AT_EPI_QT2QTR) | kind_bit(AT_EPI_RT2Q) | kind_bit(AT_EPI_RT2RTQ))) != 0;
     const int64_t gx = (n_rows + kPwCtaRows - 1) / kPwCtaRows;
     if (gx >= (1ll << 31)) return set_error(AT_ERR_UNSUPPORTED, "at_pointwise: too many rows");
     dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>((epi->n_tiles + kWarps - 1) / kWarps));
